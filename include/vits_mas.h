@@ -1,0 +1,129 @@
+/*
+ * vits_mas.h -- C ABI of libvits_mas.so: the B200 (sm_100a) replacement for the training-time
+ * alignment hot path of Aloento/VITS.
+ *
+ * Every entry point names the reference interface it replaces (file:line are into the
+ * reference tree).  Plain pointers and sizes only; no torch types.  All device entry points are
+ * asynchronous on the given stream and never synchronise; they return 0 (MAS_OK) or a negative
+ * MAS_E_* code for argument errors, or a positive cudaError_t when a launch fails.  There is no
+ * CPU fallback: without a CUDA device every compute entry fails with a cudaError.
+ *
+ * Per-utterance length errors (t_x > t_y, zero lengths -- undefined behaviour in the reference,
+ * core.pyx:13-33) cannot be reported synchronously because lengths live on the device: such an
+ * utterance gets an all-zero path and a sticky bit in the status word at the start of the
+ * scratch buffer (see mas_scratch_status_offset).
+ */
+#ifndef VITS_MAS_H
+#define VITS_MAS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mas_stream_t; /* cudaStream_t */
+
+enum {
+  MAS_OK = 0,
+  MAS_E_BAD_SHAPE = -1,   /* B, T_y, T_x <= 0 or above the supported maximum */
+  MAS_E_BAD_DTYPE = -2,   /* unknown element-type code */
+  MAS_E_NULL = -3,        /* a required pointer is NULL */
+  MAS_E_SCRATCH = -4,     /* scratch buffer smaller than mas_maximum_path_scratch_bytes() */
+  MAS_E_ALIGN = -5,       /* pointer not aligned to its element size */
+  MAS_E_UNSUPPORTED = -6  /* configuration this build has no kernel for */
+};
+
+/* Element-type codes for the mask (input) and path (output) tensors. */
+enum {
+  MAS_F32 = 0, MAS_F16 = 1, MAS_BF16 = 2, MAS_F64 = 3,
+  MAS_U8 = 4 /* also bool */, MAS_I8 = 5, MAS_I16 = 6, MAS_I32 = 7, MAS_I64 = 8
+};
+
+/* Bits of the device status word. */
+enum {
+  MAS_STATUS_TX_GT_TY = 1,   /* some utterance had t_x > t_y                     */
+  MAS_STATUS_EMPTY = 2,      /* some utterance had t_x < 1 or t_y < 1            */
+  MAS_STATUS_TOO_LONG = 4    /* some utterance had t_y > T_y or t_x > T_x        */
+};
+
+int mas_abi_version(void);
+const char* mas_error_string(int code);
+
+/* Bytes of device scratch one maximum_path call needs (direction bits, per-frame index,
+ * lengths, status word).  The caller allocates it (e.g. with torch) and may reuse it across
+ * calls on the same stream. */
+size_t mas_maximum_path_scratch_bytes(int B, int T_y, int T_x);
+/* Byte offset of the int32 status word inside the scratch buffer. */
+size_t mas_scratch_status_offset(void);
+
+/*
+ * mas_maximum_path -- replaces maximum_path_c (monotonic_align/core.pyx:36-42) together with the
+ * host marshalling around it (monotonic_align/__init__.py:14-20): the forward dynamic program over
+ * the band, the backtrack, and the materialisation of the dense 0/1 path.
+ *
+ *   neg_cent   device, float32 [B, T_y, T_x] contiguous; NOT modified (the reference works on a
+ *              host copy, __init__.py:14)
+ *   Lengths, one of:
+ *     t_ys,t_xs  device int32 [B]  (core.pyx:38 `t_ys`, `t_xs`), or
+ *     mask       device [B, T_y, T_x] view with element strides (mask_sb, mask_sy, mask_sx) of type
+ *                mask_dtype; lengths are the sums of column 0 and of row 0 exactly as
+ *                __init__.py:17-18 computes them.  Pass t_ys = t_xs = NULL to use the mask.
+ *   path_out   device [B, T_y, T_x] contiguous of type path_dtype; fully overwritten with 0/1
+ *              (replaces np.zeros + the final cast, __init__.py:15,20).  May be NULL when only
+ *              the index is wanted.
+ *   index_out  optional device int32 [B, T_y]: text position of each frame, -1 on padded frames.
+ *   scratch    device, >= mas_maximum_path_scratch_bytes(B,T_y,T_x) bytes, 16-byte aligned.
+ */
+int mas_maximum_path(const float* neg_cent,
+                     const int32_t* t_ys, const int32_t* t_xs,
+                     const void* mask, int mask_dtype, int64_t mask_sb, int64_t mask_sy, int64_t mask_sx,
+                     void* path_out, int path_dtype,
+                     int32_t* index_out,
+                     void* scratch, size_t scratch_bytes,
+                     int B, int T_y, int T_x, mas_stream_t stream);
+
+/*
+ * mas_maximum_path_c_host -- same argument meaning as the reference's native entry
+ * `maximum_path_c(int[:,:,::1] paths, float[:,:,::1] values, int[::1] t_ys, int[::1] t_xs)`
+ * (core.pyx:38) with HOST pointers: copies values to the device, runs mas_maximum_path, copies
+ * the int32 paths back, and synchronises.  `values` is left untouched (the reference clobbers
+ * its host copy; nothing reads it afterwards, __init__.py:19-20).  Uses an internal stream and
+ * cached device/pinned buffers; not re-entrant (the reference has a single caller thread).
+ * Returns 0, a MAS_E_* code, or MAS_STATUS_* bits << 8 when an utterance had invalid lengths.
+ */
+int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs,
+                            int B, int T_y, int T_x);
+/* Release the buffers cached by mas_maximum_path_c_host. */
+void mas_host_release(void);
+
+/*
+ * mas_neg_cent -- replaces the inline contraction of SynthesizerTrn.forward
+ * (SynthesizerTrn.py:223-232): neg_cent[b,t,s] = sum_d( -0.5 log 2pi - logs_p - 0.5 z_p^2 e^{-2 logs_p}
+ * + z_p m_p e^{-2 logs_p} - 0.5 m_p^2 e^{-2 logs_p} ).
+ *   z_p     device float32 [B, C, T_y]   (T_y contiguous)
+ *   m_p     device float32 [B, C, T_x]
+ *   logs_p  device float32 [B, C, T_x]
+ *   neg_cent device float32 [B, T_y, T_x], fully overwritten
+ *   scratch  device, >= mas_neg_cent_scratch_bytes(B,C,T_y,T_x) bytes, 16-byte aligned
+ */
+size_t mas_neg_cent_scratch_bytes(int B, int C, int T_y, int T_x);
+int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent,
+                 void* scratch, size_t scratch_bytes,
+                 int B, int C, int T_y, int T_x, mas_stream_t stream);
+
+/* Number of kernel launches the library has issued since load (bench.py's gpu_launches). */
+uint64_t mas_launch_count(void);
+
+/* Benchmark/tuning hooks (not part of the reference-facing surface); 0 = automatic choice.
+ * cols_per_lane in {1,2,4,8}; rows_per_stage in {8,16,32}; stages >= 2; pdl 0/1 toggles
+ * programmatic dependent launch between the three kernels. */
+void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl);
+/* neg_cent implementation: -1 automatic, 0 fp32 CUDA cores, 1 tcgen05 (split-bf16). */
+void mas_set_neg_cent_impl(int impl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITS_MAS_H */

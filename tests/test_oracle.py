@@ -1,0 +1,124 @@
+"""CPU tests: the oracle (oracle/) against the reference's golden vectors and compiled code.
+
+The oracle is the checker for the GPU parity tests, so it is pinned here first:
+  * tests/golden/mas_golden.npz / synth_golden.npz were produced by the REAL reference
+    (tests/golden/make_golden.py: its own wrapper + its own compiled Cython + its own model);
+  * when oracle/_ref is present (built from /root/reference in place) the C port is also
+    compared against the compiled reference on fresh random inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import check_path_properties, index_to_path, path_to_index, random_lengths, sha_path
+
+
+def test_oracle_matches_reference_golden(oracle, mas_golden):
+    assert len(mas_golden) >= 18
+    for name, c in mas_golden.items():
+        path = oracle.maximum_path_numpy(c["neg_cent"], c["t_ys"], c["t_xs"])
+        assert sha_path(path) == c["sha256"], name
+        np.testing.assert_array_equal(path_to_index(path), c["index"], err_msg=name)
+        check_path_properties(path, c["t_ys"], c["t_xs"])
+
+
+def test_appendix_a_known_answers(oracle, mas_golden):
+    """SURVEY.md Appendix A (captured from the compiled reference during the survey)."""
+    c = mas_golden["kat_zeros_6x3"]
+    assert c["index"][0].tolist() == [0, 1, 2, 2, 2, 2]                 # ties stay, forced diagonal
+    assert mas_golden["kat_square_5x5"]["index"][0].tolist() == [0, 1, 2, 3, 4]
+    assert mas_golden["kat_tx1_4x1"]["index"][0].tolist() == [0, 0, 0, 0]
+    k4 = mas_golden["kat_mod13_ragged"]["index"]
+    assert k4[0].tolist() == [0, 0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 4]
+    assert k4[1].tolist() == [0, 0, 0, 0, 1, 1, 2, 2, 3, -1, -1, -1]
+    assert k4[2].tolist() == [0, 0, 0, 1, 1, 2, 2, -1, -1, -1, -1, -1]
+    k5 = mas_golden["kat_mod29_ragged"]
+    assert k5["sha256"] == "fa4f108ba9b56b19f13f9213964b1a56a33065591db48c40e6f566b7924060ff"
+    p5 = index_to_path(k5["index"].astype(np.int32), 16)
+    assert p5[0].sum(0).tolist() == [1, 1, 1, 6, 1, 2, 8, 2, 1, 3, 1, 1, 12, 3, 7, 14]
+    k6 = index_to_path(mas_golden["kat_hand_4x3"]["index"].astype(np.int32), 3)
+    assert k6[0].tolist() == [[1, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]
+
+
+def test_pure_python_port_agrees(oracle, mas_golden):
+    for name in ["kat_zeros_6x3", "kat_mod13_ragged", "kat_mod29_ragged", "kat_hand_4x3", "rand_3x40x31",
+                 "ties_int_3x90x40", "huge_2x60x20"]:
+        c = mas_golden[name]
+        path = oracle.maximum_path_py(c["neg_cent"], c["t_ys"], c["t_xs"])
+        assert sha_path(path) == c["sha256"], name
+
+
+@pytest.mark.parametrize("kind", ["stock", "omp"])
+def test_c_port_vs_compiled_reference(oracle, kind):
+    core = oracle.load_ref_core(kind)
+    if core is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(99)
+    for (B, T_y, T_x) in [(4, 64, 17), (3, 257, 96), (2, 512, 192), (5, 33, 33), (2, 700, 1)]:
+        nc = (rng.standard_normal((B, T_y, T_x)) * 2 - 3).astype(np.float32)
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        ours = oracle.maximum_path_numpy(nc, t_ys, t_xs)
+        ref = oracle.maximum_path_numpy(nc, t_ys, t_xs, core=core)
+        np.testing.assert_array_equal(ours, ref)
+        check_path_properties(ours, t_ys, t_xs)
+    # integer-valued inputs (dense ties) and values below the -1e9 sentinel
+    nc = rng.integers(-3, 4, size=(3, 120, 50)).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, 3, 120, 50)
+    np.testing.assert_array_equal(oracle.maximum_path_numpy(nc, t_ys, t_xs),
+                                  oracle.maximum_path_numpy(nc, t_ys, t_xs, core=core))
+    nc = (rng.standard_normal((2, 80, 30)) * 5e8 - 1e9).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, 2, 80, 30)
+    np.testing.assert_array_equal(oracle.maximum_path_numpy(nc, t_ys, t_xs),
+                                  oracle.maximum_path_numpy(nc, t_ys, t_xs, core=core))
+
+
+def test_wrapper_contract(oracle):
+    """dtype/device follow neg_cent, input not mutated, bool mask accepted, non-contiguous rejected
+    (reference behaviour recorded in SURVEY.md Appendix A)."""
+    rng = np.random.default_rng(3)
+    nc = torch.from_numpy(rng.standard_normal((2, 30, 10)).astype(np.float32))
+    keep = nc.clone()
+    t_ys, t_xs = torch.tensor([30, 21]), torch.tensor([10, 7])
+    mask = oracle.attn_mask(t_xs, t_ys, 10, 30)
+    out = oracle.maximum_path(nc, mask.float())
+    assert out.dtype == torch.float32 and out.shape == nc.shape and torch.equal(nc, keep)
+    out_b = oracle.maximum_path(nc, mask)            # bool mask
+    assert torch.equal(out, out_b)
+    out_h = oracle.maximum_path(nc.half(), mask.float())
+    assert out_h.dtype == torch.float16
+    out_d = oracle.maximum_path(nc.double(), mask.float())
+    assert out_d.dtype == torch.float64 and torch.equal(out_d.float(), out)
+    check_path_properties(out.numpy().astype(np.int8), t_ys.numpy(), t_xs.numpy())
+    with pytest.raises(ValueError):
+        oracle.maximum_path_c(np.zeros((2, 10, 30), np.int32).transpose(0, 2, 1),
+                              np.zeros((2, 30, 10), np.float32), np.array([30, 21], np.int32),
+                              np.array([10, 7], np.int32))
+
+
+def test_neg_cent_expansion_vs_closed_form(oracle):
+    g = torch.Generator().manual_seed(5)
+    B, C, T_y, T_x = 2, 192, 70, 24
+    z = torch.randn(B, C, T_y, generator=g)
+    m = torch.randn(B, C, T_x, generator=g)
+    ls = torch.randn(B, C, T_x, generator=g) * 0.3
+    nc32 = oracle.neg_cent_torch(z, m, ls)
+    nc64 = oracle.neg_cent_f64(z.numpy(), m.numpy(), ls.numpy())
+    scale = np.abs(nc64).max()
+    assert nc32.dtype == torch.float32 and tuple(nc32.shape) == (B, T_y, T_x)
+    assert np.abs(nc32.numpy() - nc64).max() <= 1e-5 * scale
+    nc64_t = oracle.neg_cent_torch(z.double(), m.double(), ls.double()).numpy()
+    assert np.abs(nc64_t - nc64).max() <= 1e-11 * scale
+
+
+def test_oracle_vs_real_model_capture(oracle, synth_golden):
+    """One forward of the real SynthesizerTrn (config_cje.yaml, random init, CPU fp32)."""
+    s = synth_golden
+    z, m, ls = (torch.from_numpy(s[k]) for k in ("z_p", "m_p", "logs_p"))
+    nc = oracle.neg_cent_torch(z, m, ls)
+    ref = torch.from_numpy(s["neg_cent"])
+    assert (nc - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    mask = torch.from_numpy(s["x_mask"]).unsqueeze(2) * torch.from_numpy(s["spec_mask"]).unsqueeze(-1)
+    path = oracle.maximum_path(ref, mask.squeeze(1))
+    np.testing.assert_array_equal(path_to_index(path.numpy()), s["index"])
+    np.testing.assert_array_equal(mask.squeeze(1).sum(1)[:, 0].numpy().astype(np.int32), s["y_lengths"])
+    np.testing.assert_array_equal(mask.squeeze(1).sum(2)[:, 0].numpy().astype(np.int32), s["x_lengths"])

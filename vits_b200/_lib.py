@@ -1,0 +1,71 @@
+"""ctypes binding of libvits_mas.so (the C ABI in include/vits_mas.h).
+
+There is no CPU fallback: if the library cannot be built or loaded, importing the compute
+entry points raises.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+_lib = None
+
+# element-type codes (include/vits_mas.h)
+MAS_F32, MAS_F16, MAS_BF16, MAS_F64, MAS_U8, MAS_I8, MAS_I16, MAS_I32, MAS_I64 = range(9)
+MAS_STATUS_TX_GT_TY, MAS_STATUS_EMPTY, MAS_STATUS_TOO_LONG = 1, 2, 4
+
+EXPORTS = [
+    "mas_abi_version", "mas_error_string", "mas_maximum_path_scratch_bytes", "mas_scratch_status_offset",
+    "mas_maximum_path", "mas_maximum_path_c_host", "mas_host_release", "mas_neg_cent_scratch_bytes",
+    "mas_neg_cent", "mas_launch_count", "mas_set_tuning", "mas_set_neg_cent_impl",
+]
+
+
+class MasError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()  # raises when nvcc is missing
+    L = ctypes.CDLL(path)
+    c_int, c_i64, c_sz, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p
+    L.mas_abi_version.restype = c_int
+    L.mas_error_string.restype = ctypes.c_char_p
+    L.mas_error_string.argtypes = [c_int]
+    L.mas_maximum_path_scratch_bytes.restype = c_sz
+    L.mas_maximum_path_scratch_bytes.argtypes = [c_int, c_int, c_int]
+    L.mas_scratch_status_offset.restype = c_sz
+    L.mas_maximum_path.restype = c_int
+    L.mas_maximum_path.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_vp,
+                                   c_sz, c_int, c_int, c_int, c_vp]
+    L.mas_maximum_path_c_host.restype = c_int
+    L.mas_maximum_path_c_host.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int]
+    L.mas_host_release.restype = None
+    L.mas_neg_cent_scratch_bytes.restype = c_sz
+    L.mas_neg_cent_scratch_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    L.mas_neg_cent.restype = c_int
+    L.mas_neg_cent.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_int, c_int, c_int, c_int, c_vp]
+    L.mas_launch_count.restype = ctypes.c_uint64
+    L.mas_set_tuning.restype = None
+    L.mas_set_tuning.argtypes = [c_int, c_int, c_int, c_int]
+    L.mas_set_neg_cent_impl.restype = None
+    L.mas_set_neg_cent_impl.argtypes = [c_int]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mas_error_string(rc).decode()
+        raise MasError(f"{what} failed: {msg} (code {rc})")
+
+
+def launch_count() -> int:
+    return int(lib().mas_launch_count())

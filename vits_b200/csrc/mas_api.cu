@@ -1,0 +1,181 @@
+// mas_api.cu -- the extern "C" surface declared in include/vits_mas.h, plus the host-buffer
+// entry that mirrors the reference's native call maximum_path_c (monotonic_align/core.pyx:38).
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/vits_mas.h"
+#include "mas_internal.h"
+
+namespace mas {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace mas
+
+namespace {
+
+// State cached by the host entry (single caller thread, like the reference).
+struct HostCtx {
+  static constexpr int kChunks = 8;   // utterance groups pipelined over PCIe
+  static constexpr int kStreams = 3;
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  void* d_values = nullptr;
+  void* d_paths = nullptr;
+  void* d_lens = nullptr;
+  void* d_scratch = nullptr;
+  int32_t* h_status = nullptr;  // pinned, kChunks words
+  size_t cap_cells = 0, cap_lens = 0, cap_scratch = 0;
+  bool ready = false;
+} g_host;
+
+void host_release() {
+  if (g_host.d_values) cudaFree(g_host.d_values);
+  if (g_host.d_paths) cudaFree(g_host.d_paths);
+  if (g_host.d_lens) cudaFree(g_host.d_lens);
+  if (g_host.d_scratch) cudaFree(g_host.d_scratch);
+  if (g_host.h_status) cudaFreeHost(g_host.h_status);
+  for (auto& s : g_host.streams)
+    if (s) cudaStreamDestroy(s);
+  g_host = HostCtx{};
+}
+
+#define MAS_CUDA(x)                                \
+  do {                                             \
+    cudaError_t e_ = (x);                          \
+    if (e_ != cudaSuccess) return static_cast<int>(e_); \
+  } while (0)
+
+int host_prepare(size_t cells, size_t lens, size_t scratch) {
+  if (!g_host.ready) {
+    for (auto& s : g_host.streams) MAS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    MAS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_host.h_status), HostCtx::kChunks * sizeof(int32_t),
+                           cudaHostAllocDefault));
+    g_host.ready = true;
+  }
+  if (cells > g_host.cap_cells) {
+    if (g_host.d_values) cudaFree(g_host.d_values);
+    if (g_host.d_paths) cudaFree(g_host.d_paths);
+    g_host.d_values = g_host.d_paths = nullptr;
+    g_host.cap_cells = 0;
+    MAS_CUDA(cudaMalloc(&g_host.d_values, cells * 4));
+    MAS_CUDA(cudaMalloc(&g_host.d_paths, cells * 4));
+    g_host.cap_cells = cells;
+  }
+  if (lens > g_host.cap_lens) {
+    if (g_host.d_lens) cudaFree(g_host.d_lens);
+    g_host.d_lens = nullptr;
+    g_host.cap_lens = 0;
+    MAS_CUDA(cudaMalloc(&g_host.d_lens, lens * 2 * sizeof(int32_t)));
+    g_host.cap_lens = lens;
+  }
+  if (scratch > g_host.cap_scratch) {
+    if (g_host.d_scratch) cudaFree(g_host.d_scratch);
+    g_host.d_scratch = nullptr;
+    g_host.cap_scratch = 0;
+    MAS_CUDA(cudaMalloc(&g_host.d_scratch, scratch));
+    g_host.cap_scratch = scratch;
+  }
+  return MAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mas_abi_version(void) { return 1; }
+
+const char* mas_error_string(int code) {
+  switch (code) {
+    case MAS_OK: return "ok";
+    case MAS_E_BAD_SHAPE: return "bad shape (B, T_y, T_x must be positive; T_x <= 2048)";
+    case MAS_E_BAD_DTYPE: return "unknown element-type code";
+    case MAS_E_NULL: return "required pointer is NULL";
+    case MAS_E_SCRATCH: return "scratch buffer too small";
+    case MAS_E_ALIGN: return "misaligned pointer";
+    case MAS_E_UNSUPPORTED: return "no kernel for this configuration";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+size_t mas_maximum_path_scratch_bytes(int B, int T_y, int T_x) { return mas::maximum_path_scratch_bytes(B, T_y, T_x); }
+size_t mas_scratch_status_offset(void) { return 0; }
+
+int mas_maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask,
+                     int mask_dtype, int64_t mask_sb, int64_t mask_sy, int64_t mask_sx, void* path_out,
+                     int path_dtype, int32_t* index_out, void* scratch, size_t scratch_bytes, int B, int T_y,
+                     int T_x, mas_stream_t stream) {
+  return mas::maximum_path(neg_cent, t_ys, t_xs, mask, mask_dtype, mask_sb, mask_sy, mask_sx, path_out, path_dtype,
+                           index_out, scratch, scratch_bytes, B, T_y, T_x, static_cast<cudaStream_t>(stream));
+}
+
+int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs, int B,
+                            int T_y, int T_x) {
+  if (B <= 0 || T_y <= 0 || T_x <= 0) return MAS_E_BAD_SHAPE;
+  if (!paths || !values || !t_ys || !t_xs) return MAS_E_NULL;
+  const size_t plane = static_cast<size_t>(T_y) * T_x;
+  const int nch = B < HostCtx::kChunks ? B : HostCtx::kChunks;
+  const int per = (B + nch - 1) / nch;
+  const size_t sc_one = (mas::maximum_path_scratch_bytes(per, T_y, T_x) + 255) & ~size_t(255);
+  if (sc_one == 0) return MAS_E_BAD_SHAPE;
+  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * nch);
+  if (rc != MAS_OK) return rc;
+
+  float* d_values = static_cast<float*>(g_host.d_values);
+  int32_t* d_paths = static_cast<int32_t*>(g_host.d_paths);
+  int32_t* d_ty = static_cast<int32_t*>(g_host.d_lens);
+  int32_t* d_tx = d_ty + B;
+  cudaStream_t s0 = g_host.streams[0];
+  MAS_CUDA(cudaMemcpyAsync(d_ty, t_ys, B * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
+  MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
+  MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * nch, s0));
+  cudaEvent_t ready;
+  MAS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  MAS_CUDA(cudaEventRecord(ready, s0));
+  for (int i = 1; i < HostCtx::kStreams; ++i) MAS_CUDA(cudaStreamWaitEvent(g_host.streams[i], ready, 0));
+
+  // utterance groups: H2D -> kernels -> D2H, round-robin over the streams so the copies of one
+  // group overlap the kernels / opposite-direction copies of its neighbours.
+  int nused = 0;
+  for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+    const int nb = (B - b0) < per ? (B - b0) : per;
+    cudaStream_t st = g_host.streams[c % HostCtx::kStreams];
+    unsigned char* sc = static_cast<unsigned char*>(g_host.d_scratch) + sc_one * c;
+    MAS_CUDA(cudaMemcpyAsync(d_values + plane * b0, values + plane * b0, plane * nb * 4, cudaMemcpyHostToDevice, st));
+    rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0,
+                           MAS_I32, nullptr, sc, sc_one, nb, T_y, T_x, st);
+    if (rc != MAS_OK) {
+      cudaEventDestroy(ready);
+      return rc;
+    }
+    MAS_CUDA(cudaMemcpyAsync(paths + plane * b0, d_paths + plane * b0, plane * nb * 4, cudaMemcpyDeviceToHost, st));
+    MAS_CUDA(cudaMemcpyAsync(&g_host.h_status[c], sc + mas_scratch_status_offset(), sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, st));
+    nused = c + 1;
+  }
+  for (auto& s : g_host.streams) MAS_CUDA(cudaStreamSynchronize(s));
+  cudaEventDestroy(ready);
+  int status = 0;
+  for (int c = 0; c < nused; ++c) status |= g_host.h_status[c];
+  return status ? (status << 8) : MAS_OK;
+}
+
+void mas_host_release(void) { host_release(); }
+
+size_t mas_neg_cent_scratch_bytes(int B, int C, int T_y, int T_x) { return mas::neg_cent_scratch_bytes(B, C, T_y, T_x); }
+
+int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent, void* scratch,
+                 size_t scratch_bytes, int B, int C, int T_y, int T_x, mas_stream_t stream) {
+  return mas::neg_cent(z_p, m_p, logs_p, neg_cent, scratch, scratch_bytes, B, C, T_y, T_x,
+                       static_cast<cudaStream_t>(stream));
+}
+
+uint64_t mas_launch_count(void) { return mas::g_launches.load(std::memory_order_relaxed); }
+
+/* Tuning hooks for benchmarks (not part of the reference-facing surface). 0 = automatic. */
+void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl) {
+  mas::set_tuning(cols_per_lane, rows_per_stage, stages, pdl);
+}
+void mas_set_neg_cent_impl(int impl) { mas::set_neg_cent_impl(impl); }
+
+}  // extern "C"

@@ -1,0 +1,24 @@
+// Internal C++ declarations shared by the translation units of libvits_mas.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mas {
+
+void count_launch();
+
+// mas_path.cu
+int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask, int mask_dtype,
+                 int64_t msb, int64_t msy, int64_t msx, void* path_out, int path_dtype, int32_t* index_out,
+                 void* scratch, size_t scratch_bytes, int B, int T_y, int T_x, cudaStream_t st);
+size_t maximum_path_scratch_bytes(int B, int T_y, int T_x);
+void set_tuning(int K, int R, int S, int pdl);
+
+// mas_neg_cent.cu
+int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
+             int B, int C, int T_y, int T_x, cudaStream_t st);
+size_t neg_cent_scratch_bytes(int B, int C, int T_y, int T_x);
+void set_neg_cent_impl(int impl);
+
+}  // namespace mas

@@ -1,0 +1,46 @@
+"""``neg_cent(z_p, m_p, logs_p)``: the contraction SynthesizerTrn.forward computes inline
+(reference SynthesizerTrn.py:223-232), as one fused sm_100a kernel behind ``mas_neg_cent``
+(include/vits_mas.h).  fp32 in, fp32 out, independent of any surrounding autocast context."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+
+_scratch: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _scratch_for(device: torch.device, stream: int, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torch.Tensor:
+    """z_p [B,C,T_y]; m_p, logs_p [B,C,T_x]  ->  neg_cent [B,T_y,T_x] float32.
+
+    Inputs of other float dtypes (e.g. fp16 activations under autocast) are promoted to float32
+    first: the parity target is the reference's fp32 formulation."""
+    if not (z_p.is_cuda and m_p.is_cuda and logs_p.is_cuda):
+        raise ValueError("neg_cent needs CUDA tensors (there is no CPU implementation)")
+    if z_p.dim() != 3 or m_p.dim() != 3 or m_p.shape != logs_p.shape or z_p.shape[:2] != m_p.shape[:2]:
+        raise ValueError(f"bad shapes z_p {tuple(z_p.shape)} m_p {tuple(m_p.shape)} logs_p {tuple(logs_p.shape)}")
+    L = _lib.lib()
+    z, m, ls = (t.detach().float().contiguous() for t in (z_p, m_p, logs_p))
+    B, C, T_y = z.shape
+    T_x = m.shape[2]
+    dev = z.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty((B, T_y, T_x), dtype=torch.float32, device=dev)
+        nbytes = int(L.mas_neg_cent_scratch_bytes(B, C, T_y, T_x))
+        scratch = _scratch_for(dev, stream, nbytes)
+        rc = L.mas_neg_cent(z.data_ptr(), m.data_ptr(), ls.data_ptr(), out.data_ptr(), scratch.data_ptr(),
+                            scratch.numel(), B, C, T_y, T_x, stream)
+        _lib.check(rc, "mas_neg_cent")
+    return out
