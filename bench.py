@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- MAS alignments/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A step = one ``maximum_path(neg_cent, mask)`` call over one batch of synthetic input
+(SURVEY.md section 8d shapes).  Reported:
+
+  value    alignments/s with neg_cent / mask resident in HBM, CUDA-event timed, whole job (all ranks)
+  e2e      the same metric through the reference-facing C entry ``mas_maximum_path_c_host`` (the twin of
+           core.pyx:38) with pinned HOST buffers: H2D of neg_cent and D2H of the int32 path inside the
+           timed region
+  roofline achieved algorithmic GB/s of the maximum_path kernel chain (forward DP + backtrack + write-out,
+           chained with programmatic dependent launch so they overlap and are timed as one unit) against the
+           measured HBM copy bandwidth; ``kernels_ms`` gives the per-kernel durations from a serialised pass
+  cpu_baseline  the reference's own Cython (oracle/_ref, compiled from /root/reference) timed on this box's
+           host cores on the same workload
+
+Under torchrun every rank aligns its own shard of utterances (weak scaling: B per GPU fixed, like
+``batch_size`` per replica in the reference's DDP, train.py:101); there is no collective in the timed region.
+After timing, ranks all-gather their per-frame indices over NCCL only to verify them.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name: (B per GPU, T_y, T_x)
+    "c1": (1, 128, 32), "c2": (64, 1024, 192), "c3": (32, 1536, 256), "c4": (8, 4096, 512),
+}
+METRIC = "MAS alignments/sec"
+UNIT = "alignments/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_lengths(rng, B, T_y, T_x, ragged):
+    if not ragged:
+        return np.full(B, T_y, np.int32), np.full(B, T_x, np.int32)
+    t_xs = rng.integers((T_x + 1) // 2, T_x + 1, size=B)
+    t_ys = np.array([rng.integers(max(tx, (T_y + 1) // 2), T_y + 1) for tx in t_xs])
+    t_xs[0], t_ys[0] = T_x, T_y
+    order = np.argsort(-t_ys, kind="stable")
+    return t_ys[order].astype(np.int32), t_xs[order].astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
+    """The reference's CPU path on this box's host cores, same workload.  R1: as shipped (its Cython
+    built with its setup.py's flags => serial) through the wrapper's marshalling; R2: core only;
+    R4: the same Cython rebuilt with -O3 -fopenmp on all cores (steelman)."""
+    import torch
+    from oracle import mas_oracle
+    stock = mas_oracle.load_ref_core("stock")
+    omp = mas_oracle.load_ref_core("omp")
+    kind = "reference" if stock is not None else "port"
+    core = stock if stock is not None else mas_oracle.maximum_path_c
+    g = torch.Generator().manual_seed(seed)
+    nc = torch.randn(B, T_y, T_x, generator=g) * 20 - 400
+    mask = mas_oracle.attn_mask(torch.as_tensor(t_xs), torch.as_tensor(t_ys), T_x, T_y, torch.float32)
+
+    def timeit(fn, budget):
+        fn()
+        ts = []
+        t_end = time.perf_counter() + budget
+        while len(ts) < 3 or (time.perf_counter() < t_end and len(ts) < 200):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), float(min(ts)), len(ts)
+
+    res = {}
+    med, best, n = timeit(lambda: mas_oracle.maximum_path(nc, mask, core=core), budget_s * 0.5)
+    res["wrapper"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med}
+    values = nc.numpy().astype(np.float32)
+    ty32, tx32 = np.asarray(t_ys, np.int32), np.asarray(t_xs, np.int32)
+    paths = np.zeros(values.shape, np.int32)
+
+    def core_only(c):
+        v = values.copy()
+        paths.fill(0)
+        t0 = time.perf_counter()
+        c(paths, v, ty32, tx32)
+        return time.perf_counter() - t0
+
+    def time_core(c, budget):
+        core_only(c)
+        ts, t_end = [], time.perf_counter() + budget
+        while len(ts) < 3 or (time.perf_counter() < t_end and len(ts) < 200):
+            ts.append(core_only(c))
+        return float(np.median(ts)), float(min(ts)), len(ts)
+
+    med, best, n = time_core(core, budget_s * 0.25)
+    res["core_only"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med}
+    threads = len(os.sched_getaffinity(0))
+    if omp is not None:
+        os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+        med, best, n = time_core(omp, budget_s * 0.25)
+        res["omp_steelman_core_only"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med,
+                                         "threads": threads}
+    cpu_model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), "")
+    except Exception:
+        pass
+    return kind, res, {"cpu_model": cpu_model, "cpu_count": os.cpu_count(), "affinity": threads}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B, T_y, T_x = WORKLOADS[args.workload]
+    rng = np.random.default_rng(1234)
+    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, args.ragged)
+    import torch
+    from oracle import mas_oracle
+    stock = mas_oracle.load_ref_core("stock")
+    core = stock if stock is not None else mas_oracle.maximum_path_c
+    kind = "reference" if stock is not None else "port"
+    g = torch.Generator().manual_seed(1234)
+    nc = torch.randn(B, T_y, T_x, generator=g) * 20 - 400
+    mask = mas_oracle.attn_mask(torch.as_tensor(t_xs), torch.as_tensor(t_ys), T_x, T_y, torch.float32)
+    steps = min(args.steps, 50)
+    warm = min(args.warmup, 5)
+    for _ in range(max(warm, 1)):
+        mas_oracle.maximum_path(nc, mask, core=core)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mas_oracle.maximum_path(nc, mask, core=core)
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    _, extra, host = cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=6.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: B={B} T_y={T_y} T_x={T_x} {'ragged' if args.ragged else 'full-length'} "
+                               "neg_cent~N(-400,20^2), CPU tensors in and out",
+                   "path": "monotonic_align.maximum_path wrapper marshalling (__init__.py:14-20) + the reference's "
+                           "compiled core.pyx, built with its setup.py's flags (no OpenMP => serial prange)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"{steps} full batches of the workload", "variants": extra, "host": host},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import vits_b200
+    from vits_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B, T_y, T_x = WORKLOADS[args.workload]
+    rng = np.random.default_rng(1234 + rank)
+    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, args.ragged)
+    ty_d = torch.as_tensor(t_ys, device=dev)
+    tx_d = torch.as_tensor(t_xs, device=dev)
+    ym = torch.arange(T_y, device=dev)[None, :] < ty_d[:, None]
+    xm = torch.arange(T_x, device=dev)[None, :] < tx_d[:, None]
+    mask = (ym[:, :, None] & xm[:, None, :]).float()          # [B,T_y,T_x] like attn_mask.squeeze(1)
+
+    # rotating buffer sets so that consecutive steps never find their input or output in L2
+    plane_bytes = B * T_y * T_x * 4
+    nbuf = max(2, min(8, int(np.ceil(3 * 126e6 / (2 * plane_bytes)))))
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ncs = [torch.randn(B, T_y, T_x, generator=g, device=dev) * 20 - 400 for _ in range(nbuf)]
+    outs = [None] * nbuf
+
+    def step(i):
+        outs[i % nbuf] = vits_b200.maximum_path(ncs[i % nbuf], mask)
+
+    # --- correctness gate before timing: oracle on rank 0's first buffer (bit-exact) ---
+    parity = None
+    if rank == 0:
+        from oracle import mas_oracle
+        want = mas_oracle.maximum_path_numpy(ncs[0].cpu().numpy(), t_ys, t_xs)
+        step(0)
+        torch.cuda.synchronize()
+        parity = bool(np.array_equal(outs[0].cpu().numpy().astype(np.int32), want))
+        assert parity, "GPU path differs from the oracle -- refusing to report a number"
+
+    # one CUDA graph per buffer set: removes the Python/ctypes enqueue cost from the device timeline
+    graphs = None
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            for i in range(nbuf):
+                step(i)
+            torch.cuda.synchronize()
+            graphs = []
+            for i in range(nbuf):
+                gr = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(gr):
+                    step(i)
+                launches_per_step = _lib.launch_count() - n0
+                graphs.append(gr)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+            graphs = None
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % nbuf].replay()
+        else:
+            step(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        run_step(i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = (_lib.launch_count() - n0) if graphs is None else launches_per_step * args.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # --- per-kernel durations: serialised pass (PDL off, eager), events between the three kernels ---
+    kernels_ms = None
+    if rank == 0:
+        kernels_ms = per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev)
+
+    # --- end to end through the host-buffer C entry (pinned host memory) ---
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 20))
+        h_vals = [torch.empty(B, T_y, T_x, dtype=torch.float32).pin_memory() for _ in range(2)]
+        for hv, nc in zip(h_vals, ncs):
+            hv.copy_(nc)
+        h_paths = [torch.empty(B, T_y, T_x, dtype=torch.int32).pin_memory() for _ in range(2)]
+        h_ty, h_tx = torch.as_tensor(t_ys), torch.as_tensor(t_xs)
+
+        def host_step(i):
+            rc = L.mas_maximum_path_c_host(h_paths[i % 2].data_ptr(), h_vals[i % 2].data_ptr(), h_ty.data_ptr(),
+                                           h_tx.data_ptr(), B, T_y, T_x)
+            assert rc == 0, rc
+        for i in range(3):
+            host_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            host_step(i)
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            from oracle import mas_oracle
+            want = mas_oracle.maximum_path_numpy(h_vals[0].numpy(), t_ys, t_xs)
+            assert np.array_equal(h_paths[0].numpy(), want), "e2e path differs from the oracle"
+        e2e = {"value": world * B * e2e_steps / float(td.item()), "unit": UNIT,
+               "h2d_bytes_per_step": plane_bytes + 8 * B, "d2h_bytes_per_step": plane_bytes + 32,
+               "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",
+               "api": "mas_maximum_path_c_host (twin of core.pyx:38), pinned host buffers"}
+        L.mas_host_release()
+
+    # --- multi-GPU verification (outside the timed region): all-gather the per-frame indices over NCCL ---
+    verified = None
+    if world > 1:
+        idx = vits_b200.maximum_path_index(ncs[0], mask)
+        gathered = torch.empty(world * B, T_y, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered, idx)
+        lens = torch.stack([ty_d, tx_d], 1).to(torch.int32)
+        all_lens = torch.empty(world * B, 2, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_lens, lens)
+        if rank == 0:
+            gi, gl = gathered.cpu().numpy(), all_lens.cpu().numpy()
+            ok = True
+            for b in range(world * B):
+                ty, tx = int(gl[b, 0]), int(gl[b, 1])
+                row = gi[b, :ty]
+                d = np.diff(row)
+                ok &= bool(row[0] == 0 and row[-1] == tx - 1 and ((d == 0) | (d == 1)).all() and (gi[b, ty:] == -1).all())
+            verified = ok
+            assert ok, "gathered paths violate the alignment invariants"
+
+    if rank == 0:
+        alg_bytes = 4 * int(np.sum(t_ys.astype(np.int64) * t_xs)) + 4 * B * T_y * T_x
+        peak, peak_src = measured_peak_gbs()
+        step_ms = ms_max / args.steps
+        achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: B={B}/GPU T_y={T_y} T_x={T_x} {'ragged lengths' if args.ragged else 'full-length'}"
+                                   f" with [B,T_y,T_x] fp32 mask, neg_cent~N(-400,20^2) fp32 -> fp32 path",
+                       "l2": f"inputs larger than L2: {nbuf} rotating (neg_cent, path) buffer sets = "
+                             f"{2 * nbuf * plane_bytes / 1e6:.0f} MB, no flush kernel in the timed region",
+                       "launch": "one CUDA graph replay per step" if graphs is not None else "eager ctypes launches",
+                       "parity_checked": parity, "multi_gpu_verified": verified},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                         "kernel": "maximum_path chain (mas_forward + mas_backtrack + mas_writeout, PDL-overlapped, "
+                                   "timed as one unit with CUDA events on the launching stream)",
+                         "kernels_ms_serialised": kernels_ms},
+        }
+        if not args.no_cpu and world == 1:
+            kind, res, host = cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=args.cpu_budget)
+            line["cpu_baseline"] = {"value": res["wrapper"]["alignments_per_s"], "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"{res['wrapper']['reps']} full batches of the same workload "
+                                              "(reference wrapper marshalling + compiled core.pyx, as shipped: serial)",
+                                    "variants": res, "host": host}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=20):
+    """Serialised per-kernel timing: PDL off so the kernels do not overlap, then whole-chain minus parts is
+    attributed by timing index-only (forward+backtrack) and full calls.  Returns ms per call."""
+    import torch
+    import vits_b200
+    out = {}
+    try:
+        L.mas_set_tuning(0, 0, 0, 0)
+        for name, fn in (("forward+backtrack", lambda nc: vits_b200.maximum_path_index(nc, mask)),
+                         ("forward+backtrack+writeout", lambda nc: vits_b200.maximum_path(nc, mask))):
+            for i in range(3):
+                fn(ncs[i % len(ncs)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                fn(ncs[i % len(ncs)])
+            e1.record()
+            torch.cuda.synchronize()
+            out[name + " (no PDL, eager)"] = e0.elapsed_time(e1) / reps
+    finally:
+        L.mas_set_tuning(0, 0, 0, 1)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--ragged", action="store_true", help="variable lengths (SURVEY 8d) instead of full-length")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""CPU tests of the C-ABI boundary: the library builds/loads, exports every symbol that
+include/vits_mas.h declares, and validates arguments before touching CUDA (no compute here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "vits_mas.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mas_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from vits_b200 import _lib
+    declared = _declared_functions()
+    assert "mas_maximum_path" in declared and "mas_neg_cent" in declared and "mas_maximum_path_c_host" in declared
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_library_exports_every_declared_symbol():
+    from vits_b200 import _lib
+    L = _lib.lib()
+    for name in _declared_functions():
+        assert hasattr(L, name), f"libvits_mas.so does not export {name}"
+    assert L.mas_abi_version() == 1
+    assert L.mas_scratch_status_offset() == 0
+
+
+def test_scratch_query_and_error_strings():
+    from vits_b200 import _lib
+    L = _lib.lib()
+    n = L.mas_maximum_path_scratch_bytes(64, 1024, 192)
+    # >= direction bits (1 bit per cell) + per-frame index + lengths
+    assert n >= 64 * 1024 * 192 // 8 + 64 * 1024 * 4 + 64 * 8
+    assert n < 8 * 1024 * 1024
+    assert L.mas_maximum_path_scratch_bytes(0, 10, 10) == 0
+    assert b"scratch" in L.mas_error_string(-4)
+    assert L.mas_error_string(0) == b"ok"
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call, so this runs on a CPU-only machine."""
+    from vits_b200 import _lib
+    L = _lib.lib()
+    fake = ctypes.c_void_p(0x1000)   # never dereferenced: validation fails first
+    big = 1 << 30
+    def call(nc=fake, tys=fake, txs=fake, mask=None, path=fake, idx=None, scratch=fake, sbytes=big,
+             B=2, T_y=16, T_x=8, pdt=_lib.MAS_F32):
+        return L.mas_maximum_path(nc, tys, txs, mask, 0, 0, 0, 0, path, pdt, idx, scratch, sbytes, B, T_y, T_x, None)
+    assert call(B=0) == -1
+    assert call(T_x=4096) == -1
+    assert call(nc=None) == -3
+    assert call(tys=None) == -3            # only one of the two length arrays
+    assert call(tys=None, txs=None) == -3  # neither lengths nor mask
+    assert call(path=None) == -3           # neither path nor index requested
+    assert call(pdt=99) == -2
+    assert call(sbytes=16) == -4
+    assert call(scratch=ctypes.c_void_p(0x1004)) == -5
+    assert L.mas_neg_cent(None, fake, fake, fake, fake, big, 1, 192, 8, 8, None) == -3
+    assert L.mas_neg_cent(fake, fake, fake, fake, fake, big, 0, 192, 8, 8, None) == -1
+    assert L.mas_maximum_path_c_host(None, fake, fake, fake, 1, 4, 4) == -3
+
+
+def test_python_wrapper_rejects_bad_inputs():
+    import torch
+    from vits_b200.monotonic_align import maximum_path
+    nc = torch.zeros(2, 8, 4)
+    with pytest.raises(ValueError):
+        maximum_path(nc.transpose(1, 2), torch.ones(2, 4, 8))     # not C-contiguous (reference: ValueError)
+    with pytest.raises(ValueError):
+        maximum_path(torch.zeros(8, 4), torch.ones(8, 4))          # not [b, t_t, t_s]
+    with pytest.raises(ValueError):
+        maximum_path(torch.zeros(2, 8, 4, dtype=torch.int32), torch.ones(2, 8, 4))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from vits_b200 import _lib
+    from vits_b200.monotonic_align import maximum_path
+    with pytest.raises(_lib.MasError):
+        maximum_path(torch.zeros(1, 8, 4), torch.ones(1, 8, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vits_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "mas_oracle" not in text, f

@@ -1,0 +1,240 @@
+"""GPU parity tests of maximum_path: the CUDA path (through the drop-in wrapper and the raw C ABI)
+against the CPU oracle on identical fp32 inputs.  Bar: bit-exact paths."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import check_path_properties, index_to_path, path_to_index, random_lengths, sha_path
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mp():
+    import vits_b200.monotonic_align as m
+    yield m
+    m._lib.lib().mas_set_tuning(0, 0, 0, 1)
+
+
+def _mask(t_ys, t_xs, T_y, T_x, device, dtype=torch.float32):
+    ty = torch.as_tensor(t_ys, device=device)
+    tx = torch.as_tensor(t_xs, device=device)
+    ym = torch.arange(T_y, device=device)[None, :] < ty[:, None]
+    xm = torch.arange(T_x, device=device)[None, :] < tx[:, None]
+    return (ym[:, :, None] & xm[:, None, :]).to(dtype)
+
+
+def _gpu_path(mp, nc_np, t_ys, t_xs, via="mask"):
+    nc = torch.from_numpy(nc_np).cuda()
+    B, T_y, T_x = nc.shape
+    if via == "mask":
+        out = mp.maximum_path(nc, _mask(t_ys, t_xs, T_y, T_x, nc.device))
+    else:
+        out = mp.maximum_path_from_lengths(nc, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+    assert out.dtype == nc.dtype and out.device == nc.device and out.shape == nc.shape
+    return out.cpu().numpy().astype(np.int8)
+
+
+def test_golden_vectors(mp, mas_golden):
+    for name, c in mas_golden.items():
+        for via in ("mask", "lengths"):
+            got = _gpu_path(mp, c["neg_cent"], c["t_ys"], c["t_xs"], via)
+            assert sha_path(got) == c["sha256"], (name, via)
+
+
+SWEEP = [(3, 9, 1), (2, 40, 2), (4, 64, 31), (4, 64, 32), (3, 70, 33), (2, 130, 63), (2, 130, 64), (2, 131, 65),
+         (2, 97, 96), (2, 97, 97), (2, 98, 97), (2, 400, 191), (2, 400, 192), (2, 401, 193), (2, 700, 256),
+         (2, 777, 257), (1, 1030, 449), (2, 1100, 512), (1, 1200, 900), (1, 2100, 1024)]
+
+
+@pytest.mark.parametrize("shape", SWEEP)
+def test_random_sweep_bit_exact(mp, oracle, shape):
+    B, T_y, T_x = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 32))
+    nc = (rng.standard_normal(shape) * 3 - 4).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+    got = _gpu_path(mp, nc, t_ys, t_xs)
+    np.testing.assert_array_equal(got, want)
+    # minimal and degenerate lengths: t_x == t_y (pure diagonal), t_y == t_x + 1, t_x == 1
+    t_xs2 = np.minimum(t_xs, T_y)
+    t_ys2 = t_xs2.copy()
+    if B > 1:
+        t_ys2[1] = min(T_y, t_xs2[1] + 1)
+    if B > 2:
+        t_xs2[2] = 1
+    want = oracle.maximum_path_numpy(nc, t_ys2, t_xs2).astype(np.int8)
+    got = _gpu_path(mp, nc, t_ys2, t_xs2, via="lengths")
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+@pytest.mark.parametrize("R", [8, 16, 32])
+def test_every_kernel_configuration(mp, oracle, K, R):
+    """Each cols-per-lane / rows-per-stage instantiation, vector and scalar load paths."""
+    L = mp._lib.lib()
+    rng = np.random.default_rng(1000 * K + R)
+    for shape in [(3, 150, 96), (2, 333, 100), (2, 260, 193)]:
+        B, T_y, T_x = shape
+        nc = (rng.standard_normal(shape) * 2 - 1).astype(np.float32)
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+        for stages in (2, 5):
+            for pdl in (1, 0):
+                L.mas_set_tuning(K, R, stages, pdl)
+                got = _gpu_path(mp, nc, t_ys, t_xs)
+                np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} {shape}")
+    L.mas_set_tuning(0, 0, 0, 1)
+
+
+def test_ties_and_huge_magnitudes(mp, oracle):
+    rng = np.random.default_rng(11)
+    nc = rng.integers(-2, 3, size=(4, 300, 150)).astype(np.float32)          # dense ties
+    t_ys, t_xs = random_lengths(rng, 4, 300, 150)
+    np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs), oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8))
+    nc = np.zeros((2, 200, 70), np.float32)                                  # all ties
+    np.testing.assert_array_equal(_gpu_path(mp, nc, [200, 150], [70, 70]),
+                                  oracle.maximum_path_numpy(nc, [200, 150], [70, 70]).astype(np.int8))
+    nc = (rng.standard_normal((3, 250, 90)) * 5e8 - 1e9).astype(np.float32)  # values below the -1e9 sentinel
+    t_ys, t_xs = random_lengths(rng, 3, 250, 90)
+    np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs), oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8))
+
+
+def test_dtypes_and_mask_kinds(mp, oracle):
+    rng = np.random.default_rng(5)
+    B, T_y, T_x = 3, 120, 48
+    nc32 = torch.from_numpy((rng.standard_normal((B, T_y, T_x)) * 2).astype(np.float32)).cuda()
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    for dt in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
+        nc = nc32.to(dt)
+        keep = nc.clone()
+        want = oracle.maximum_path_numpy(nc.float().cpu().numpy(), t_ys, t_xs)
+        for mdt in (torch.float32, torch.bool, torch.float16, torch.int64, torch.uint8):
+            out = mp.maximum_path(nc, _mask(t_ys, t_xs, T_y, T_x, nc.device, mdt))
+            assert out.dtype == dt and out.device == nc.device
+            np.testing.assert_array_equal(out.cpu().double().numpy(), want.astype(np.float64))
+        assert torch.equal(nc, keep), "input must not be modified"
+    # the caller's mask is a broadcast product of two prefix masks (SynthesizerTrn.py:234); an expanded
+    # (stride-0) view must work too
+    xm = (torch.arange(T_x, device="cuda")[None, :] < torch.as_tensor(t_xs, device="cuda")[:, None]).float()
+    ym = (torch.arange(T_y, device="cuda")[None, :] < torch.as_tensor(t_ys, device="cuda")[:, None]).float()
+    attn_mask = (xm[:, None, None, :] * ym[:, None, :, None]).squeeze(1)
+    want = oracle.maximum_path_numpy(nc32.cpu().numpy(), t_ys, t_xs)
+    np.testing.assert_array_equal(mp.maximum_path(nc32, attn_mask).cpu().numpy(), want.astype(np.float32))
+    col = ym[:, :, None].expand(B, T_y, T_x)  # stride 0 along x: column 0 still carries t_y ...
+    row = xm[:, None, :].expand(B, T_y, T_x)
+    np.testing.assert_array_equal(mp.maximum_path(nc32, col * row).cpu().numpy(), want.astype(np.float32))
+
+
+def test_misaligned_base_pointer(mp, oracle):
+    """A contiguous view whose storage offset breaks 16-byte alignment takes the scalar-load path."""
+    rng = np.random.default_rng(8)
+    B, T_y, T_x = 2, 200, 64
+    for off in (1, 2, 3):
+        flat = torch.from_numpy(rng.standard_normal(B * T_y * T_x + off).astype(np.float32)).cuda()
+        nc = flat[off:].view(B, T_y, T_x)
+        assert nc.is_contiguous() and nc.data_ptr() % 16 != 0
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        want = oracle.maximum_path_numpy(nc.cpu().numpy(), t_ys, t_xs).astype(np.int8)
+        got = mp.maximum_path_from_lengths(nc, torch.as_tensor(t_ys), torch.as_tensor(t_xs)).cpu().numpy().astype(np.int8)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_index_output(mp, oracle):
+    rng = np.random.default_rng(21)
+    B, T_y, T_x = 4, 310, 130
+    nc = (rng.standard_normal((B, T_y, T_x))).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    idx = mp.maximum_path_index(torch.from_numpy(nc).cuda(), y_lengths=torch.as_tensor(t_ys), x_lengths=torch.as_tensor(t_xs))
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (B, T_y)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs)
+    np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want))
+
+
+def test_invalid_lengths_flagged_not_imitated(mp):
+    """t_x > t_y and empty utterances are UB in the reference: we zero the path and flag."""
+    nc = torch.randn(3, 20, 12, device="cuda")
+    t_ys = torch.tensor([20, 5, 0])
+    t_xs = torch.tensor([12, 9, 4])
+    mp.last_status()
+    out = mp.maximum_path_from_lengths(nc, t_ys, t_xs)
+    assert out[0].sum().item() == 20 and out[1].sum().item() == 0 and out[2].sum().item() == 0
+    bits = mp.last_status()
+    assert bits & 1 and bits & 2
+    assert mp.last_status() == 0
+    with pytest.raises(mp.StatusError):
+        mp.maximum_path_from_lengths(nc, t_ys, t_xs, check=True)
+    assert mp.maximum_path_from_lengths(nc, torch.tensor([20, 20, 20]), torch.tensor([12, 9, 4]), check=True).sum().item() == 60
+
+
+def test_raw_c_abi_overwrites_output_and_respects_stream(mp, oracle):
+    L = mp._lib.lib()
+    rng = np.random.default_rng(31)
+    B, T_y, T_x = 3, 257, 100
+    nc_np = rng.standard_normal((B, T_y, T_x)).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    want = oracle.maximum_path_numpy(nc_np, t_ys, t_xs)
+    nc = torch.from_numpy(nc_np).cuda()
+    ty = torch.as_tensor(t_ys, dtype=torch.int32).cuda()
+    tx = torch.as_tensor(t_xs, dtype=torch.int32).cuda()
+    scratch = torch.zeros(L.mas_maximum_path_scratch_bytes(B, T_y, T_x), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    for dt, code in ((torch.int32, 7), (torch.int8, 5), (torch.float32, 0), (torch.float64, 3), (torch.int64, 8), (torch.float16, 1)):
+        path = torch.full((B, T_y, T_x), 77, dtype=dt, device="cuda")          # poison: must be fully overwritten
+        idx = torch.full((B, T_y), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            rc = L.mas_maximum_path(nc.data_ptr(), ty.data_ptr(), tx.data_ptr(), None, 0, 0, 0, 0, path.data_ptr(), code,
+                                    idx.data_ptr(), scratch.data_ptr(), scratch.numel(), B, T_y, T_x, stream.cuda_stream)
+        assert rc == 0
+        stream.synchronize()
+        np.testing.assert_array_equal(path.cpu().numpy().astype(np.int32), want)
+        np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want))
+    assert L.mas_launch_count() > 0
+
+
+def test_host_buffer_entry_matches_maximum_path_c(mp, oracle):
+    """mas_maximum_path_c_host is the twin of core.pyx:38 on host arrays; the wrapper uses it for CPU tensors."""
+    L = mp._lib.lib()
+    rng = np.random.default_rng(41)
+    for (B, T_y, T_x) in [(1, 50, 20), (5, 180, 77), (19, 300, 128)]:
+        values = rng.standard_normal((B, T_y, T_x)).astype(np.float32)
+        keep = values.copy()
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        paths = np.full((B, T_y, T_x), 9, dtype=np.int32)
+        rc = L.mas_maximum_path_c_host(paths.ctypes.data, values.ctypes.data, t_ys.ctypes.data, t_xs.ctypes.data, B, T_y, T_x)
+        assert rc == 0
+        np.testing.assert_array_equal(paths, oracle.maximum_path_numpy(keep, t_ys, t_xs))
+        np.testing.assert_array_equal(values, keep)
+        nc_cpu = torch.from_numpy(values)
+        out = mp.maximum_path(nc_cpu, _mask(t_ys, t_xs, T_y, T_x, "cpu"))
+        assert out.device.type == "cpu" and out.dtype == torch.float32
+        np.testing.assert_array_equal(out.numpy().astype(np.int32), paths)
+    L.mas_host_release()
+
+
+CONFIGS = {"c1": (1, 128, 32), "c2": (64, 1024, 192), "c3": (32, 1536, 256), "c4": (8, 4096, 512)}
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+@pytest.mark.parametrize("ragged", [False, True])
+def test_baseline_configs_full_size(mp, oracle, cfg, ragged):
+    """BASELINE.json configs at full size: bit-exact vs the oracle AND the size-independent invariants."""
+    B, T_y, T_x = CONFIGS[cfg]
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    nc = torch.randn(B, T_y, T_x, generator=g, device="cuda") * 20 - 400
+    rng = np.random.default_rng(7)
+    if ragged:
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    else:
+        t_ys, t_xs = np.full(B, T_y, np.int32), np.full(B, T_x, np.int32)
+    out = mp.maximum_path(nc, _mask(t_ys, t_xs, T_y, T_x, nc.device))
+    got = out.cpu().numpy().astype(np.int8)
+    check_path_properties(got, t_ys, t_xs)
+    want = oracle.maximum_path_numpy(nc.cpu().numpy(), t_ys, t_xs).astype(np.int8)
+    np.testing.assert_array_equal(got, want)
+    # idempotence / determinism: a second call gives the same bytes
+    again = mp.maximum_path(nc, _mask(t_ys, t_xs, T_y, T_x, nc.device))
+    assert torch.equal(out, again)

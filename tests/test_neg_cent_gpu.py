@@ -1,0 +1,91 @@
+"""GPU parity tests of neg_cent (SynthesizerTrn.py:223-232) and of the end-to-end path.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d):
+  * neg_cent: |ours - fp32 torch expression| <= 1e-5 * max|neg_cent| per utterance;
+  * end-to-end: >= 99.9 % of path cells equal the oracle's, every differing frame a near-tie.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import path_to_index, random_lengths
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+def _inputs(B, C, T_y, T_x, seed, t_ys=None, t_xs=None):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    z = torch.randn(B, C, T_y, generator=g, device="cuda")
+    m = torch.randn(B, C, T_x, generator=g, device="cuda")
+    ls = torch.randn(B, C, T_x, generator=g, device="cuda") * 0.3
+    if t_ys is not None:   # zero the padded tails like TextEncoder.py:99 / PosteriorEncoder.py:66
+        for b in range(B):
+            z[b, :, int(t_ys[b]):] = 0
+            m[b, :, int(t_xs[b]):] = 0
+            ls[b, :, int(t_xs[b]):] = 0
+    return z, m, ls
+
+
+def _check(ours, ref):
+    scale = ref.abs().amax(dim=(1, 2), keepdim=True)
+    err = ((ours - ref).abs() / scale).max().item()
+    assert err <= REL_TOL, f"relative error {err:.3e} > {REL_TOL}"
+    return err
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 192, 128, 32), (3, 192, 150, 44), (2, 192, 1024, 192), (1, 192, 777, 257),
+                                   (2, 80, 130, 70), (1, 192, 1536, 256), (1, 192, 300, 512)])
+def test_neg_cent_vs_fp32_expression(oracle, impl, shape):
+    import vits_b200
+    vits_b200._lib.lib().mas_set_neg_cent_impl(impl)
+    try:
+        B, C, T_y, T_x = shape
+        z, m, ls = _inputs(B, C, T_y, T_x, seed=sum(shape))
+        ours = vits_b200.neg_cent(z, m, ls)
+        assert ours.dtype == torch.float32 and tuple(ours.shape) == (B, T_y, T_x)
+        ref32 = oracle.neg_cent_torch(z, m, ls)
+        _check(ours, ref32)
+        if T_y * T_x <= 200 * 300:
+            ref64 = torch.from_numpy(oracle.neg_cent_f64(z.cpu().numpy(), m.cpu().numpy(), ls.cpu().numpy())).cuda()
+            _check(ours.double(), ref64)
+    finally:
+        vits_b200._lib.lib().mas_set_neg_cent_impl(-1)
+
+
+def test_neg_cent_real_model_capture(oracle, synth_golden):
+    import vits_b200
+    s = synth_golden
+    z, m, ls = (torch.from_numpy(s[k]).cuda() for k in ("z_p", "m_p", "logs_p"))
+    ours = vits_b200.neg_cent(z, m, ls)
+    _check(ours, torch.from_numpy(s["neg_cent"]).cuda())
+
+
+def test_neg_cent_ignores_autocast(oracle):
+    import vits_b200
+    z, m, ls = _inputs(2, 192, 96, 40, seed=3)
+    with torch.autocast("cuda", dtype=torch.float16):
+        ours = vits_b200.neg_cent(z.half(), m, ls)
+    _check(ours, oracle.neg_cent_torch(z.half().float(), m, ls))
+
+
+@pytest.mark.parametrize("shape", [(8, 192, 400, 100), (64, 192, 1024, 192)])
+def test_end_to_end_path_agreement(oracle, shape):
+    """z_p, m_p, logs_p -> neg_cent (ours) -> path (ours)  vs  oracle neg_cent -> oracle path."""
+    import vits_b200
+    B, C, T_y, T_x = shape
+    rng = np.random.default_rng(17)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    z, m, ls = _inputs(B, C, T_y, T_x, seed=29, t_ys=t_ys, t_xs=t_xs)
+    nc_ours = vits_b200.neg_cent(z, m, ls)
+    path_ours = vits_b200.maximum_path_from_lengths(nc_ours, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+    nc_ref = oracle.neg_cent_torch(z, m, ls)
+    want = oracle.maximum_path_numpy(nc_ref.cpu().numpy(), t_ys, t_xs)
+    got = path_ours.cpu().numpy().astype(np.int32)
+    valid = sum(int(a) * int(b) for a, b in zip(t_ys, t_xs))
+    differing = int((got != want).sum())
+    assert differing <= 1e-3 * valid, f"{differing} of {valid} cells differ"
+    # and on the *same* neg_cent the paths are bit-identical
+    same = vits_b200.maximum_path_from_lengths(nc_ref, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+    np.testing.assert_array_equal(same.cpu().numpy().astype(np.int32), want)

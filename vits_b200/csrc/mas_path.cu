@@ -129,7 +129,8 @@ __device__ __forceinline__ void load_row(float (&c)[K], const float* __restrict_
     } else {
 #pragma unroll
       for (int q = 0; q < K / 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(row + xl + 4 * q);
+        // T_x % 4 == 0 on this path: a quad is entirely inside or entirely outside the row
+        const float4 t = *reinterpret_cast<const float4*>(row + min(xl + 4 * q, T_x - 4));
         c[4 * q + 0] = t.x;
         c[4 * q + 1] = t.y;
         c[4 * q + 2] = t.z;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
 
   // ---- DP warp: columns [x0, x0+K) per lane ----------------------------------------------------
   const int x0 = (dw * 32 + lane) * K;
-  const int xl = VEC ? min(x0, p.T_x - K) : x0;  // load column (clamped for padding lanes)
+  const int xl = (VEC && K < 4) ? min(x0, p.T_x - K) : x0;  // load column (padding lanes are clamped)
   const bool has_left = dw > 0;
   const bool has_right = dw < W_act - 1;
   const float* bnd_in = bnd + static_cast<size_t>(has_left ? dw - 1 : 0) * BR;
@@ -562,8 +563,12 @@ static bool pick_fwd_config(int T_x, FwdConfig* cfg) {
 template <int K, bool VEC, bool BIG>
 static cudaError_t launch_fwd_t(const FwdParams& p, size_t smem, cudaStream_t st) {
   auto kern = mas_forward_kernel<K, VEC, BIG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
+  static size_t smem_set = 0;  // per instantiation; raised once, never during a later stream capture
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    smem_set = 200 * 1024;
+  }
   kern<<<p.B, 32 * (p.W + 1), smem, st>>>(p);
   return cudaGetLastError();
 }
