@@ -370,9 +370,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
-                         "kernel": "maximum_path chain (mas_forward + mas_backtrack + mas_writeout, PDL-overlapped, "
+                         "kernel": "maximum_path chain (mas_forward with fused backtrack + mas_writeout, PDL-overlapped, "
                                    "timed as one unit with CUDA events on the launching stream)",
-                         "kernels_ms_serialised": kernels_ms},
+                         "phase_timeline_us": kernels_ms},
         }
         if not args.no_cpu and world == 1:
             kind, res, host = cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=args.cpu_budget)
@@ -385,28 +385,39 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=20):
-    """Serialised per-kernel timing: PDL off so the kernels do not overlap, then whole-chain minus parts is
-    attributed by timing index-only (forward+backtrack) and full calls.  Returns ms per call."""
+def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=5):
+    """Phase timeline of one call from %globaltimer stamps written by the kernels themselves
+    (mas_set_timeline): microseconds relative to the first forward CTA's start, median of `reps`."""
     import torch
     import vits_b200
+    names = ["fwd_first_start", "fwd_last_dp_done", "fwd_last_end(backtrack tail done)", "bt_first_start", "bt_last_end",
+             "wo_first_start", "wo_last_zero_fill_done", "wo_last_end"]
+    tl = torch.zeros(8, dtype=torch.int64, device=dev)
     out = {}
     try:
-        L.mas_set_tuning(0, 0, 0, 0)
-        for name, fn in (("forward+backtrack", lambda nc: vits_b200.maximum_path_index(nc, mask)),
-                         ("forward+backtrack+writeout", lambda nc: vits_b200.maximum_path(nc, mask))):
-            for i in range(3):
-                fn(ncs[i % len(ncs)])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(reps):
-                fn(ncs[i % len(ncs)])
-            e1.record()
-            torch.cuda.synchronize()
-            out[name + " (no PDL, eager)"] = e0.elapsed_time(e1) / reps
+        for pdl in (1, 0):
+            L.mas_set_tuning(0, 0, 0, pdl)
+            runs = []
+            for i in range(reps + 1):
+                tl.zero_()
+                tl[0] = tl[3] = tl[5] = -1
+                torch.cuda.synchronize()
+                L.mas_set_timeline(tl.data_ptr())
+                vits_b200.maximum_path(ncs[i % len(ncs)], mask)
+                torch.cuda.synchronize()
+                L.mas_set_timeline(None)
+                v = tl.cpu().numpy().astype(np.uint64)
+                runs.append([(int(x) - int(v[0])) / 1e3 if int(x) not in (0, 2 ** 64 - 1) else None for x in v])
+            runs = runs[1:]
+            med = {}
+            for k, n in enumerate(names):
+                vals = [r[k] for r in runs if r[k] is not None]
+                if vals:
+                    med[n] = float(np.median(vals))
+            out["pdl" if pdl else "serialised"] = med
     finally:
         L.mas_set_tuning(0, 0, 0, 1)
+        L.mas_set_timeline(None)
     return out
 
 

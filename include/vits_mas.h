@@ -122,6 +122,14 @@ uint64_t mas_launch_count(void);
 void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl);
 /* neg_cent implementation: -1 automatic, 0 fp32 CUDA cores, 1 tcgen05 (split-bf16). */
 void mas_set_neg_cent_impl(int impl);
+/* Benchmark isolation: bit0 forward DP, bit1 backtrack, bit2 write-out; default 7 (all). */
+void mas_set_debug_kernels(int mask);
+/* fused: -1 automatic, 0 separate backtrack kernel, 1 backtrack fused into the forward kernel;
+ * helpers: helper warps of the fused kernel (0 = automatic). */
+void mas_set_tuning2(int fused, int helpers);
+/* Debug timeline: device pointer to 8 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
+ * kernels update with min start / max end %globaltimer stamps; NULL disables. */
+void mas_set_timeline(void* dev_ptr);
 
 #ifdef __cplusplus
 }

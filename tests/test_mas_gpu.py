@@ -16,6 +16,7 @@ def mp():
     import vits_b200.monotonic_align as m
     yield m
     m._lib.lib().mas_set_tuning(0, 0, 0, 1)
+    m._lib.lib().mas_set_tuning2(-1, 0)
 
 
 def _mask(t_ys, t_xs, T_y, T_x, device, dtype=torch.float32):
@@ -81,12 +82,13 @@ def test_every_kernel_configuration(mp, oracle, K, R):
         nc = (rng.standard_normal(shape) * 2 - 1).astype(np.float32)
         t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
         want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
-        for stages in (2, 5):
-            for pdl in (1, 0):
-                L.mas_set_tuning(K, R, stages, pdl)
-                got = _gpu_path(mp, nc, t_ys, t_xs)
-                np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} {shape}")
+        for stages, pdl, fused, helpers in ((2, 1, 0, 0), (5, 0, 0, 0), (3, 1, 1, 1), (4, 0, 1, 4), (0, 1, -1, 0)):
+            L.mas_set_tuning(K, R, stages, pdl)
+            L.mas_set_tuning2(fused, helpers)
+            got = _gpu_path(mp, nc, t_ys, t_xs)
+            np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} fused={fused} {shape}")
     L.mas_set_tuning(0, 0, 0, 1)
+    L.mas_set_tuning2(-1, 0)
 
 
 def test_ties_and_huge_magnitudes(mp, oracle):

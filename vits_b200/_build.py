@@ -1,17 +1,21 @@
-"""Build libvits_mas.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libvits_mas.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+Each .cu is compiled to an object in parallel, then linked."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+OBJ = os.path.join(_HERE, "build")
 LIB_PATH = os.path.join(_HERE, "libvits_mas.so")
-SOURCES = ["mas_path.cu", "mas_neg_cent.cu", "mas_neg_cent_tc.cu", "mas_api.cu"]
+SOURCES = ["mas_path.cu", "mas_fwd_k1.cu", "mas_fwd_k2.cu", "mas_fwd_k4.cu", "mas_fwd_k8.cu", "mas_neg_cent.cu",
+           "mas_neg_cent_tc.cu", "mas_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
     "--fmad=true",   # FMA contraction is fine for neg_cent; the DP has no multiply to contract
 ]
 
@@ -23,27 +27,52 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libvits_mas.so cannot be built (no CPU fallback exists)")
 
 
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(os.path.dirname(_HERE), "include", "vits_mas.h")]
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(os.path.dirname(_HERE), "include", "vits_mas.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def _compile_one(nvcc, src, obj, verbose):
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    return cmd, out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    out = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or out.returncode != 0:
-        print(" ".join(cmd))
-        print(out.stdout)
-        print(out.stderr)
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    headers_mtime = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
+    jobs = []
+    for s in srcs:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), headers_mtime)
+        jobs.append((src, obj, stale))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose) if j[2] else (None, None), jobs))
+    for cmd, out in results:
+        if out is None:
+            continue
+        if verbose or out.returncode != 0:
+            print(" ".join(cmd))
+            print(out.stdout)
+            print(out.stderr)
+        if out.returncode != 0:
+            raise RuntimeError("nvcc failed building libvits_mas.so")
+    link = [nvcc, "-shared", "-o", LIB_PATH] + [j[1] for j in jobs]
+    out = subprocess.run(link, capture_output=True, text=True)
     if out.returncode != 0:
-        raise RuntimeError("nvcc failed building libvits_mas.so")
+        print(out.stdout, out.stderr)
+        raise RuntimeError("linking libvits_mas.so failed")
     return LIB_PATH
 
 

@@ -177,5 +177,8 @@ void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl) 
   mas::set_tuning(cols_per_lane, rows_per_stage, stages, pdl);
 }
 void mas_set_neg_cent_impl(int impl) { mas::set_neg_cent_impl(impl); }
+void mas_set_debug_kernels(int mask) { mas::set_debug_kernels(mask); }
+void mas_set_tuning2(int fused, int helpers) { mas::set_tuning2(fused, helpers); }
+void mas_set_timeline(void* dev_ptr) { mas::set_timeline(static_cast<unsigned long long*>(dev_ptr)); }
 
 }  // extern "C"

@@ -14,6 +14,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
                  void* scratch, size_t scratch_bytes, int B, int T_y, int T_x, cudaStream_t st);
 size_t maximum_path_scratch_bytes(int B, int T_y, int T_x);
 void set_tuning(int K, int R, int S, int pdl);
+void set_debug_kernels(int mask);
+void set_tuning2(int fused, int helpers);
+void set_timeline(unsigned long long* dev_ptr);
 
 // mas_neg_cent.cu
 int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,

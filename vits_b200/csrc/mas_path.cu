@@ -29,320 +29,11 @@
 // and at x==0 exactly as core.pyx:17-27; ties stay (strict <); index==y forces a step.
 #include <cstdint>
 #include <cstdio>
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
-#include "../../include/vits_mas.h"
-#include "mas_internal.h"
-#include "ptx_sm100.cuh"
+#include "mas_forward.cuh"
 
 namespace mas {
-
-constexpr float kNeg = -1e9f;  // core.pyx:7 max_neg_val
-
-// ------------------------------------------------------------------------------------------------
-// lengths from the mask, as monotonic_align/__init__.py:17-18: t_y = sum_y mask[b,y,0],
-// t_x = sum_x mask[b,0,x]; float sums are truncated like numpy's astype(int32).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mask_at(const void* p, int dtype, int64_t off) {
-  switch (dtype) {
-    case MAS_F32: return static_cast<const float*>(p)[off];
-    case MAS_F16: return __half2float(static_cast<const __half*>(p)[off]);
-    case MAS_BF16: return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[off]);
-    case MAS_F64: return static_cast<const double*>(p)[off];
-    case MAS_U8: return static_cast<const uint8_t*>(p)[off];
-    case MAS_I8: return static_cast<const int8_t*>(p)[off];
-    case MAS_I16: return static_cast<const int16_t*>(p)[off];
-    case MAS_I32: return static_cast<const int32_t*>(p)[off];
-    default: return static_cast<double>(static_cast<const int64_t*>(p)[off]);
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: forward DP
-// ------------------------------------------------------------------------------------------------
-struct FwdParams {
-  const float* nc;
-  const int32_t* t_ys;
-  const int32_t* t_xs;
-  const void* mask;
-  int mask_dtype;
-  int64_t msb, msy, msx;
-  int32_t* lens;    // [B][2] = (t_y, t_x), (0,0) when invalid
-  int32_t* status;  // sticky MAS_STATUS_* bits
-  uint32_t* bits;   // [B][G][TXP]
-  int B, T_y, T_x;
-  int R;            // frames per ring stage (multiple of 8)
-  int S;            // ring stages
-  int W;            // DP warps covering the padded T_x
-  int TXP;          // W*32*K
-  int G;            // ceil(T_y/32)
-  int BR;           // hand-off ring length in frames (power of two >= (S+1)*R)
-  uint32_t slot_bytes;
-};
-
-template <int K, bool HEAD>
-__device__ __forceinline__ void row_step(float (&v)[K], uint32_t (&acc)[K], const float (&c)[K], float edge,
-                                         int y, int x0, int lane) {
-  float left = __shfl_up_sync(0xffffffffu, v[K - 1], 1);
-  if (lane == 0) left = edge;
-  if (HEAD) {
-    // diagonal: the "stay" candidate value[y-1][y] is the sentinel (core.pyx:17-18).  That cell is
-    // outside the band, so overwriting the register copy is harmless.
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-      if (x0 + j == y) v[j] = kNeg;
-  }
-#pragma unroll
-  for (int j = K - 1; j >= 1; --j) {
-    const float d = v[j] - v[j - 1];                          // sign bit == (stay < step)
-    acc[j] = __funnelshift_l(__float_as_uint(d), acc[j], 1);  // acc = (acc << 1) | sign
-    v[j] = c[j] + fmaxf(v[j - 1], v[j]);                      // core.pyx:28
-  }
-  const float d = v[0] - left;
-  acc[0] = __funnelshift_l(__float_as_uint(d), acc[0], 1);
-  v[0] = c[0] + fmaxf(left, v[0]);
-  if (HEAD) {
-    // index == y forces a step in the backtrack (core.pyx:32): fold it into the stored bit.
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-      if (x0 + j == y) acc[j] |= 1u;
-  }
-}
-
-template <int K, bool VEC>
-__device__ __forceinline__ void load_row(float (&c)[K], const float* __restrict__ row, int xl, int T_x) {
-  if (VEC) {
-    if (K == 1) {
-      c[0] = row[xl];
-    } else if (K == 2) {
-      const float2 t = *reinterpret_cast<const float2*>(row + xl);
-      c[0] = t.x;
-      c[1] = t.y;
-    } else {
-#pragma unroll
-      for (int q = 0; q < K / 4; ++q) {
-        // T_x % 4 == 0 on this path: a quad is entirely inside or entirely outside the row
-        const float4 t = *reinterpret_cast<const float4*>(row + min(xl + 4 * q, T_x - 4));
-        c[4 * q + 0] = t.x;
-        c[4 * q + 1] = t.y;
-        c[4 * q + 2] = t.z;
-        c[4 * q + 3] = t.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < K; ++j) c[j] = row[min(xl + j, T_x - 1)];
-  }
-}
-
-// BIG: more than 7 DP warps (block of up to 1024 threads, 64 registers each); otherwise the
-// block has at most 256 threads and the compiler may use the full register file per thread.
-template <int K, bool VEC, bool BIG>
-__global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const FwdParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const int S = p.S, R = p.R, W = p.W, BR = p.BR;
-
-  // smem carve-up
-  float* ring = reinterpret_cast<float*>(smem);
-  float* bnd = reinterpret_cast<float*>(smem + static_cast<size_t>(S) * p.slot_bytes);  // [(W-1)][BR]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bnd + static_cast<size_t>(max(W - 1, 1)) * BR);
-  uint64_t* full = bars;             // [S]
-  uint64_t* empty = bars + S;        // [S]
-  uint64_t* bfull = bars + 2 * S;    // [(W-1)][S]
-  double* red = reinterpret_cast<double*>(bfull + static_cast<size_t>(max(W - 1, 1)) * S);  // [2][32]
-  int* lens_s = reinterpret_cast<int*>(red + 64);                                            // [2]
-
-  // Let the dependent kernels (backtrack, write-out) get scheduled right away: the write-out's
-  // zero-fill does not depend on us.
-  ptx::pdl_launch_dependents();
-
-  // ---- lengths -------------------------------------------------------------------------------
-  if (p.t_ys != nullptr) {
-    if (tid == 0) {
-      lens_s[0] = p.t_ys[b];
-      lens_s[1] = p.t_xs[b];
-    }
-  } else {
-    double sy = 0.0, sx = 0.0;
-    const int64_t base = static_cast<int64_t>(b) * p.msb;
-    for (int y = tid; y < p.T_y; y += blockDim.x) sy += mask_at(p.mask, p.mask_dtype, base + y * p.msy);
-    for (int x = tid; x < p.T_x; x += blockDim.x) sx += mask_at(p.mask, p.mask_dtype, base + x * p.msx);
-    sy = warp_sum(sy);
-    sx = warp_sum(sx);
-    if (lane == 0) {
-      red[warp] = sy;
-      red[32 + warp] = sx;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int nw = blockDim.x >> 5;
-      sy = warp_sum(lane < nw ? red[lane] : 0.0);
-      sx = warp_sum(lane < nw ? red[32 + lane] : 0.0);
-      if (lane == 0) {
-        lens_s[0] = static_cast<int>(sy);
-        lens_s[1] = static_cast<int>(sx);
-      }
-    }
-  }
-  __syncthreads();
-  int t_y = lens_s[0], t_x = lens_s[1];
-  {
-    int st = 0;
-    if (t_y < 1 || t_x < 1) st |= MAS_STATUS_EMPTY;
-    if (t_y > p.T_y || t_x > p.T_x) st |= MAS_STATUS_TOO_LONG;
-    if (t_x > t_y) st |= MAS_STATUS_TX_GT_TY;
-    if (st) {
-      if (tid == 0) {
-        atomicOr(p.status, st);
-        p.lens[2 * b] = 0;
-        p.lens[2 * b + 1] = 0;
-      }
-      return;  // whole CTA: the path of this utterance stays all-zero
-    }
-  }
-  const int W_act = (t_x + 32 * K - 1) / (32 * K);  // DP warps that own a column < t_x
-  if (tid == 0) {
-    p.lens[2 * b] = t_y;
-    p.lens[2 * b + 1] = t_x;
-    for (int s = 0; s < S; ++s) {
-      ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], W_act);
-    }
-    for (int i = 0; i < (W - 1) * S; ++i) ptx::mbar_init(&bfull[i], 1);
-    ptx::mbar_fence_init();
-  }
-  // hand-off slot of frame 0: the "step" candidate of frame 0 at a warp's first column is the
-  // virtual value[-1][x-1] = sentinel.
-  if (tid < W - 1) bnd[static_cast<size_t>(tid) * BR] = kNeg;
-  __syncthreads();
-
-  const float* nc_b = p.nc + static_cast<size_t>(b) * p.T_y * p.T_x;
-  const uint32_t lead_bytes = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(nc_b) & 15u);
-  const int nchunks = (t_y + R - 1) / R;
-  const size_t slot_floats = p.slot_bytes / 4;
-
-  if (warp == 0) {
-    // ---- producer: stream the utterance's frames into the ring ------------------------------
-    if (lane == 0) {
-      const unsigned char* src0 = reinterpret_cast<const unsigned char*>(nc_b) - lead_bytes;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % S;
-        if (c >= S) ptx::mbar_wait(&empty[s], ((c / S) - 1) & 1);
-        const int rows = min(R, t_y - c * R);
-        const uint32_t bytes = (lead_bytes + static_cast<uint32_t>(rows) * p.T_x * 4u + 15u) & ~15u;
-        ptx::mbar_arrive_expect_tx(&full[s], bytes);
-        ptx::bulk_g2s(reinterpret_cast<unsigned char*>(ring) + static_cast<size_t>(s) * p.slot_bytes,
-                      src0 + static_cast<size_t>(c) * R * p.T_x * 4u, bytes, &full[s]);
-      }
-    }
-    return;
-  }
-
-  const int dw = warp - 1;
-  if (dw >= W_act) return;
-
-  // ---- DP warp: columns [x0, x0+K) per lane ----------------------------------------------------
-  const int x0 = (dw * 32 + lane) * K;
-  const int xl = (VEC && K < 4) ? min(x0, p.T_x - K) : x0;  // load column (padding lanes are clamped)
-  const bool has_left = dw > 0;
-  const bool has_right = dw < W_act - 1;
-  const float* bnd_in = bnd + static_cast<size_t>(has_left ? dw - 1 : 0) * BR;
-  float* bnd_out = bnd + static_cast<size_t>(has_right ? dw : 0) * BR;
-  const bool st_lane = has_right && lane == 31;
-  uint32_t* bits_b = p.bits + static_cast<size_t>(b) * p.G * p.TXP + x0;
-
-  float v[K];
-  uint32_t acc[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    v[j] = kNeg;
-    acc[j] = 0u;
-  }
-
-  auto flush_bits = [&](int g, int nrows) {
-    uint32_t* dst = bits_b + static_cast<size_t>(g) * p.TXP;
-    const int sh = 32 - nrows;
-    if (x0 == 0) acc[0] = 0u;  // the backtrack never leaves column 0 (core.pyx:32 `index != 0`)
-    if (K % 4 == 0) {
-#pragma unroll
-      for (int q = 0; q < K / 4; ++q)
-        *reinterpret_cast<uint4*>(dst + 4 * q) =
-            make_uint4(acc[4 * q] << sh, acc[4 * q + 1] << sh, acc[4 * q + 2] << sh, acc[4 * q + 3] << sh);
-    } else if (K == 2) {
-      *reinterpret_cast<uint2*>(dst) = make_uint2(acc[0] << sh, acc[1] << sh);
-    } else {
-#pragma unroll
-      for (int j = 0; j < K; ++j) dst[j] = acc[j] << sh;
-    }
-  };
-
-  int y = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % S;
-    const uint32_t par = (c / S) & 1;
-    ptx::mbar_wait(&full[s], par);
-    if (has_left) ptx::mbar_wait(&bfull[(dw - 1) * S + s], par);
-    const float* slot = ring + static_cast<size_t>(s) * slot_floats + (lead_bytes >> 2);
-    const int rows = min(R, t_y - c * R);
-    int r = 0;
-    for (; r + 8 <= rows; r += 8, y += 8) {
-      float cc[8][K];
-      float e[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) load_row<K, VEC>(cc[i], slot + static_cast<size_t>(r + i) * p.T_x, xl, p.T_x);
-      const int sl = y & (BR - 1);
-      if (has_left) {
-        const float4 e0 = *reinterpret_cast<const float4*>(bnd_in + sl);
-        const float4 e1 = *reinterpret_cast<const float4*>(bnd_in + sl + 4);
-        e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w;
-        e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = kNeg;
-        if (y == 0) e[0] = 0.0f;  // core.pyx:22-23: the step candidate at (0,0) is 0
-      }
-      if (y < t_x) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          row_step<K, true>(v, acc, cc[i], e[i], y + i, x0, lane);
-          if (st_lane) bnd_out[(sl + i + 1) & (BR - 1)] = v[K - 1];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          row_step<K, false>(v, acc, cc[i], e[i], y + i, x0, lane);
-          if (st_lane) bnd_out[(sl + i + 1) & (BR - 1)] = v[K - 1];
-        }
-      }
-      if (((y + 8) & 31) == 0) flush_bits(y >> 5, 32);
-    }
-    for (; r < rows; ++r, ++y) {  // < 8 leftover frames of the last chunk
-      float c1[K];
-      load_row<K, VEC>(c1, slot + static_cast<size_t>(r) * p.T_x, xl, p.T_x);
-      const int sl = y & (BR - 1);
-      const float e1 = has_left ? bnd_in[sl] : (y == 0 ? 0.0f : kNeg);
-      row_step<K, true>(v, acc, c1, e1, y, x0, lane);
-      if (st_lane) bnd_out[(sl + 1) & (BR - 1)] = v[K - 1];
-      if (((y + 1) & 31) == 0) flush_bits(y >> 5, 32);
-    }
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&empty[s]);
-    if (st_lane) ptx::mbar_arrive(&bfull[dw * S + s]);
-  }
-  if (t_y & 31) flush_bits(t_y >> 5, t_y & 31);
-}
 
 // ------------------------------------------------------------------------------------------------
 // K2: backtrack (core.pyx:30-33) from the decision bits
@@ -354,14 +45,8 @@ struct BtParams {
   int T_y, TXP, G;
   int GS;   // groups per shared-memory segment
   int TXS;  // shared-memory row stride (words) of a segment
+  unsigned long long* tl;
 };
-
-// One backtrack step (core.pyx:32-33) given the decision word of the current column.  The
-// forward kernel already folded `index == y` (bit forced to 1) and `index != 0` (column 0
-// forced to 0) into the stored bits.
-__device__ __forceinline__ int bt_step(int cur, int r, uint32_t word) {
-  return cur - static_cast<int>((word >> (31 - r)) & 1u);
-}
 
 __global__ void __launch_bounds__(1024, 1) mas_backtrack_kernel(const BtParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -376,6 +61,7 @@ __global__ void __launch_bounds__(1024, 1) mas_backtrack_kernel(const BtParams p
 
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();  // forward kernel finished, its bits and lengths are visible
+  if (tid == 0) tl_min(p.tl, 3);
 
   const int t_y = p.lens[2 * b], t_x = p.lens[2 * b + 1];
   int32_t* idx_b = p.index + static_cast<size_t>(b) * p.T_y;
@@ -435,6 +121,7 @@ __global__ void __launch_bounds__(1024, 1) mas_backtrack_kernel(const BtParams p
     for (int y = y_lo + tid; y < y_hi; y += nthr) idx_b[y] = sidx[y - y_lo];
     __syncthreads();
   }
+  if (tid == 0) tl_max(p.tl, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +134,7 @@ struct WoParams {
   int T_x;
   int es;                // element size in bytes
   unsigned long long one;  // bit pattern of 1 in the element type
+  unsigned long long* tl;
 };
 
 __device__ __forceinline__ void store_elem(unsigned char* p, int es, unsigned long long bits) {
@@ -460,6 +148,7 @@ __device__ __forceinline__ void store_elem(unsigned char* p, int es, unsigned lo
 
 __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
   const int tid = threadIdx.x;
+  if (tid == 0) tl_min(p.tl, 5);
   const long long per = (p.rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = min(p.rows, per * blockIdx.x);
   const long long r1 = min(p.rows, r0 + per);
@@ -487,18 +176,22 @@ __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
     for (; i < n4; i += blockDim.x) a4[i] = z;
   }
   // phase B: the ones.  Same CTA wrote the zeros of these rows; the barrier orders them.
+  if (tid == 0) tl_max(p.tl, 6);
   ptx::pdl_wait();
   __syncthreads();
   for (long long r = r0 + tid; r < r1; r += blockDim.x) {
     const int x = p.index[r];
     if (x >= 0) store_elem(p.out + (static_cast<size_t>(r) * p.T_x + x) * p.es, p.es, p.one);
   }
+  if (tid == 0) tl_max(p.tl, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1;
+static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
+static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only)
+static unsigned long long* g_timeline = nullptr;
 
 struct Layout {
   int G, TXP_max;
@@ -520,70 +213,80 @@ static Layout scratch_layout(int B, int T_y, int T_x) {
 }
 
 struct FwdConfig {
-  int K, W, R, S, BR;
+  int K, W, H, R, S, BR, fused;
   uint32_t slot_bytes;
-  size_t smem;
+  FwdSmem sm;
 };
 
-static size_t fwd_smem_bytes(int W, int R, int S, int BR, uint32_t slot_bytes) {
+static FwdSmem fwd_smem_layout(int W, int S, int BR, uint32_t slot_bytes, int G, int TXP, bool fused) {
+  auto up = [](uint32_t v) { return (v + 127u) & ~127u; };
   const int wb = W - 1 > 1 ? W - 1 : 1;
-  return static_cast<size_t>(S) * slot_bytes + static_cast<size_t>(wb) * BR * 4 + (2 * S + static_cast<size_t>(wb) * S) * 8 +
-         64 * 8 + 16;
+  FwdSmem m{};
+  m.ring = 0;
+  m.bnd = up(static_cast<uint32_t>(S) * slot_bytes);
+  m.bars = up(m.bnd + static_cast<uint32_t>(W + 1) * BR * 4u);
+  m.red = up(m.bars + (2u * S + static_cast<uint32_t>(wb) * S + (fused ? G : 0)) * 8u);
+  m.sbits = up(m.red + 64u * 8u + 16u);
+  if (fused) {
+    m.sexit = up(m.sbits + static_cast<uint32_t>(G) * TXP * 4u);
+    m.sentry = up(m.sexit + static_cast<uint32_t>(G) * TXP * 2u);
+    m.sidx = up(m.sentry + static_cast<uint32_t>(G) * 4u);
+    m.total = up(m.sidx + static_cast<uint32_t>(G) * 32u * 2u);
+  } else {
+    m.sexit = m.sentry = m.sidx = m.sbits;
+    m.total = m.sbits;
+  }
+  return m;
 }
 
-static bool pick_fwd_config(int T_x, FwdConfig* cfg) {
-  const size_t budget = 200 * 1024;
+static bool pick_fwd_config(int T_y, int T_x, FwdConfig* cfg) {
+  const uint32_t budget = 200 * 1024;
   int K = g_tune_K;
-  // keep the block at <= 7 DP warps (<= 256 threads) so the DP warps get a full register budget
+  // keep the block small: <= 7 warps besides the producer get the full register budget
   if (K == 0) K = T_x <= 32 ? 1 : (T_x <= 448 ? 2 : (T_x <= 896 ? 4 : 8));
   int W = (T_x + 32 * K - 1) / (32 * K);
-  while (W > 31 && K < 8) {
+  while (W > 27 && K < 8) {
     K *= 2;
     W = (T_x + 32 * K - 1) / (32 * K);
   }
-  if (W > 31) return false;
-  for (int R = g_tune_R ? g_tune_R : 32; R >= 8; R >>= 1) {
-    const uint32_t slot = (static_cast<uint32_t>(R) * T_x * 4u + 16u + 15u) & ~15u;
-    int S = g_tune_S ? g_tune_S : 8;
-    for (; S >= 2; --S) {
-      int BR = 8;
-      while (BR < (S + 1) * R) BR <<= 1;
-      const size_t smem = fwd_smem_bytes(W, R, S, BR, slot);
-      if (smem <= budget) {
-        if (S < 3 && R > 8 && !g_tune_R) break;  // prefer more, smaller stages
-        *cfg = FwdConfig{K, W, R, S, BR, slot, smem};
-        return true;
-      }
+  if (W > 27) return false;
+  if (g_tune_R && g_tune_R != 8 && g_tune_R != 16 && g_tune_R != 32) return false;
+  const int G = (T_y + 31) / 32;
+  const int TXP = W * 32 * K;
+  // first choice: fused (bits + exit tables in shared memory, >= 3 ring stages); else unfused
+  for (int fused = (g_tune_fused == 0 ? 0 : 1); fused >= (g_tune_fused == 1 ? 1 : 0); --fused) {
+    int H = 0;
+    if (fused) {
+      H = g_tune_H ? g_tune_H : 4;
+      if (W <= 7 && W + H > 7) H = 7 - W;  // stay within 256 threads when possible ...
+      if (H < 1) H = g_tune_H ? g_tune_H : 2;  // ... else take the 1024-thread (64-register) variant
     }
-    if (g_tune_R) break;
+    for (int R = g_tune_R ? g_tune_R : 32; R >= 8; R >>= 1) {
+      const uint32_t slot = (static_cast<uint32_t>(R) * T_x * 4u + 16u + 15u) & ~15u;
+      for (int S = g_tune_S ? g_tune_S : (fused ? 6 : 8); S >= 2; --S) {
+        int BR = 8;
+        while (BR < (S + 1) * R) BR <<= 1;
+        if (static_cast<uint64_t>(S) * slot + (fused ? static_cast<uint64_t>(G) * TXP * 6 : 0) > budget) continue;
+        const FwdSmem m = fwd_smem_layout(W, S, BR, slot, G, TXP, fused != 0);
+        if (m.total <= budget) {
+          if (S < 3 && R > 8 && !g_tune_R) break;  // prefer more, smaller stages
+          if (fused && S < 3) break;
+          *cfg = FwdConfig{K, W, H, R, S, BR, fused, slot, m};
+          return true;
+        }
+      }
+      if (g_tune_R) break;
+    }
   }
   return false;
 }
 
-template <int K, bool VEC, bool BIG>
-static cudaError_t launch_fwd_t(const FwdParams& p, size_t smem, cudaStream_t st) {
-  auto kern = mas_forward_kernel<K, VEC, BIG>;
-  static size_t smem_set = 0;  // per instantiation; raised once, never during a later stream capture
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    smem_set = 200 * 1024;
-  }
-  kern<<<p.B, 32 * (p.W + 1), smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-template <int K, bool VEC>
-static cudaError_t launch_fwd(const FwdParams& p, size_t smem, cudaStream_t st) {
-  return p.W > 7 ? launch_fwd_t<K, VEC, true>(p, smem, st) : launch_fwd_t<K, VEC, false>(p, smem, st);
-}
-
-static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, size_t smem, cudaStream_t st) {
+static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int R, cudaStream_t st) {
   switch (K) {
-    case 1: return launch_fwd<1, true>(p, smem, st);  // K==1 loads are scalar either way
-    case 2: return vec ? launch_fwd<2, true>(p, smem, st) : launch_fwd<2, false>(p, smem, st);
-    case 4: return vec ? launch_fwd<4, true>(p, smem, st) : launch_fwd<4, false>(p, smem, st);
-    case 8: return vec ? launch_fwd<8, true>(p, smem, st) : launch_fwd<8, false>(p, smem, st);
+    case 1: return launch_fwd_k1(vec, p, R, st);
+    case 2: return launch_fwd_k2(vec, p, R, st);
+    case 4: return launch_fwd_k4(vec, p, R, st);
+    case 8: return launch_fwd_k8(vec, p, R, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -628,7 +331,7 @@ static int g_num_sms = 0;
 int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask, int mask_dtype,
                  int64_t msb, int64_t msy, int64_t msx, void* path_out, int path_dtype, int32_t* index_out,
                  void* scratch, size_t scratch_bytes, int B, int T_y, int T_x, cudaStream_t st) {
-  if (B <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || T_y > (1 << 20) || T_x > 65535) return MAS_E_BAD_SHAPE;
+  if (B <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || T_y > (1 << 20)) return MAS_E_BAD_SHAPE;
   if (!neg_cent || !scratch) return MAS_E_NULL;
   if ((t_ys == nullptr) != (t_xs == nullptr)) return MAS_E_NULL;
   if (!t_ys && !mask) return MAS_E_NULL;
@@ -642,7 +345,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   const Layout L = scratch_layout(B, T_y, T_x);
   if (scratch_bytes < L.total) return MAS_E_SCRATCH;
   FwdConfig fc;
-  if (!pick_fwd_config(T_x, &fc)) return MAS_E_UNSUPPORTED;
+  if (!pick_fwd_config(T_y, T_x, &fc)) return MAS_E_UNSUPPORTED;
 
   unsigned char* sc = static_cast<unsigned char*>(scratch);
   int32_t* status = reinterpret_cast<int32_t*>(sc + L.off_status);
@@ -650,39 +353,40 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   int32_t* index = index_out ? index_out : reinterpret_cast<int32_t*>(sc + L.off_index);
   uint32_t* bits = reinterpret_cast<uint32_t*>(sc + L.off_bits);
 
-  // K1
+  // K1: forward (+ backtrack when fused)
   FwdParams fp{};
   fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
   fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
-  fp.lens = lens; fp.status = status; fp.bits = bits;
+  fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
   fp.B = B; fp.T_y = T_y; fp.T_x = T_x;
-  fp.R = fc.R; fp.S = fc.S; fp.W = fc.W; fp.TXP = fc.W * 32 * fc.K; fp.G = L.G; fp.BR = fc.BR;
-  fp.slot_bytes = fc.slot_bytes;
+  fp.S = fc.S; fp.W = fc.W; fp.H = fc.H; fp.TXP = fc.W * 32 * fc.K; fp.G = L.G; fp.BR = fc.BR;
+  fp.fused = fc.fused; fp.slot_bytes = fc.slot_bytes; fp.sm = fc.sm;
   const bool vec = (reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0 && T_x >= fc.K;
-  cudaError_t e = launch_fwd_dispatch(fc.K, vec, fp, fc.smem, st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  count_launch();
+  cudaError_t e = cudaSuccess;
+  if (g_debug_kernels & 1) {
+    e = launch_fwd_dispatch(fc.K, vec, fp, fc.R, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    count_launch();
+  }
 
-  // K2
-  BtParams bp{};
-  bp.bits = bits; bp.lens = lens; bp.index = index;
-  bp.T_y = T_y; bp.TXP = fp.TXP; bp.G = L.G;
-  bp.TXS = T_x | 1;  // odd stride: neighbouring groups hit different banks in phase 3
-  {
+  // K2: backtrack (only when the decision bits did not fit in shared memory)
+  if (!fc.fused && (g_debug_kernels & 2)) {
+    BtParams bp{};
+    bp.bits = bits; bp.lens = lens; bp.index = index; bp.tl = g_timeline;
+    bp.T_y = T_y; bp.TXP = fp.TXP; bp.G = L.G;
+    bp.TXS = T_x | 1;  // odd stride: neighbouring groups hit different banks in phase 3
     const size_t per_group = static_cast<size_t>(bp.TXS) * 6 + 32 * 4 + 4;
     int GS = static_cast<int>((160 * 1024) / per_group);
     if (GS > L.G) GS = L.G;
     if (GS < 1) return MAS_E_UNSUPPORTED;
     bp.GS = GS;
-  }
-  const size_t bt_smem = static_cast<size_t>(bp.GS) * bp.TXS * 6 + (bp.GS + 1) * 4 + static_cast<size_t>(bp.GS) * 32 * 4 + 64;
-  static bool bt_attr = false;
-  if (!bt_attr) {
-    e = cudaFuncSetAttribute(mas_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    bt_attr = true;
-  }
-  {
+    const size_t bt_smem = static_cast<size_t>(bp.GS) * bp.TXS * 6 + (bp.GS + 1) * 4 + static_cast<size_t>(bp.GS) * 32 * 4 + 64;
+    static bool bt_attr = false;
+    if (!bt_attr) {
+      e = cudaFuncSetAttribute(mas_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      bt_attr = true;
+    }
     long long tasks = static_cast<long long>(bp.GS) * T_x;
     int threads = tasks >= 1024 ? 1024 : static_cast<int>((tasks + 31) / 32 * 32);
     if (threads < 64) threads = 64;
@@ -691,8 +395,8 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     count_launch();
   }
 
-  // K3
-  if (path_out) {
+  // K3: dense path
+  if (path_out && (g_debug_kernels & 4)) {
     if (g_num_sms == 0) {
       int dev = 0;
       cudaGetDevice(&dev);
@@ -702,6 +406,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     WoParams wp{};
     wp.out = static_cast<unsigned char*>(path_out);
     wp.index = index;
+    wp.tl = g_timeline;
     wp.rows = static_cast<long long>(B) * T_y;
     wp.T_x = T_x;
     wp.es = es;
@@ -720,11 +425,18 @@ size_t maximum_path_scratch_bytes(int B, int T_y, int T_x) {
   return scratch_layout(B, T_y, T_x).total;
 }
 
+void set_debug_kernels(int mask) { g_debug_kernels = mask; }
+void set_timeline(unsigned long long* dev_ptr) { g_timeline = dev_ptr; }
+
 void set_tuning(int K, int R, int S, int pdl) {
   g_tune_K = K;
   g_tune_R = R;
   g_tune_S = S;
   g_tune_pdl = pdl;
+}
+void set_tuning2(int fused, int helpers) {
+  g_tune_fused = fused;
+  g_tune_H = helpers;
 }
 
 }  // namespace mas
