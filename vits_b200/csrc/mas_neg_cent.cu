@@ -128,18 +128,19 @@ static int g_impl = -1;  // -1 auto
 void set_neg_cent_impl(int impl) { g_impl = impl; }
 
 size_t neg_cent_scratch_bytes(int B, int C, int T_y, int T_x) {
-  (void)B; (void)C; (void)T_y; (void)T_x;
-  return 256;
+  if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0) return 0;
+  return neg_cent_tc_scratch_bytes(B, C, T_y, T_x) + 256;
 }
 
 int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
              int B, int C, int T_y, int T_x, cudaStream_t st) {
-  (void)scratch; (void)scratch_bytes;
   if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0 || B > 65535) return MAS_E_BAD_SHAPE;
   if (!z_p || !m_p || !logs_p || !out) return MAS_E_NULL;
   if ((reinterpret_cast<uintptr_t>(z_p) | reinterpret_cast<uintptr_t>(m_p) | reinterpret_cast<uintptr_t>(logs_p) |
        reinterpret_cast<uintptr_t>(out)) & 3u)
     return MAS_E_ALIGN;
+  // impl 1 (default): tcgen05 tensor-core GEMM with split-bf16 operands; impl 0: fp32 CUDA cores
+  if (g_impl != 0) return neg_cent_tc(z_p, m_p, logs_p, out, scratch, scratch_bytes, B, C, T_y, T_x, st);
   dim3 grid((T_x + TN - 1) / TN, (T_y + TM - 1) / TM, B);
   if (grid.y > 65535) return MAS_E_BAD_SHAPE;
   neg_cent_simt_kernel<<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x);
