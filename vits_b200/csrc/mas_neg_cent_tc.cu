@@ -20,17 +20,21 @@
 //        warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=T_x tile, K=16) --
 //                    6 operand pairs x 2 k-steps per 32-channel stage; tcgen05.commit frees the
 //                    stage and publishes the accumulator
-//        warps 2-5   epilogue: tcgen05.ld the accumulator (TMEM -> registers), add the bias,
+//        warps 2-9   epilogue: tcgen05.ld the accumulator (TMEM -> registers), add the bias,
 //                    store the fp32 rows; double-buffered TMEM so it overlaps the next tile's MMAs
-//        warps 6-13  A producers: read z_p (coalesced along frames), form -0.5 z^2 and z, split to
-//                    bf16 hi/lo and write the four A operand tiles straight into the MMA layout
-//                    (the transform is why A cannot simply be TMA-loaded)
+//        warps 10-13 z loaders: read z_p (coalesced along frames) into an fp32 staging ring
+//        warps 14-21 converters: form -0.5 z^2 and z, split to bf16 hi/lo (integer rounding) and write
+//                    the four A operand tiles straight into the MMA layout, fence.proxy.async, arrive
+//                    (the transform is why A cannot simply be TMA-loaded; loaders and converters are
+//                    separate warps because the proxy fence waits for a thread's outstanding loads)
 //
 // Operand tiles use the canonical K-major SWIZZLE_NONE layout: 8-row x 16-byte core matrices,
 // address(row, k) = (k/8)*LBO + (row/8)*128 + (row%8)*16 + (k%8)*2, i.e. [k/8][row][k%8]; with
 // 16-byte chunks contiguous along rows both our producer stores and the tensor core reads are
 // bank-conflict free, so no swizzle is needed.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -42,30 +46,51 @@ namespace mas {
 
 namespace tc {
 constexpr int M = 128;            // frames per tile (UMMA M)
-constexpr int CB = 32;            // channels per pipeline stage
-constexpr int STAGES = 2;
+constexpr int CB = 16;            // channels per pipeline stage (one UMMA k-step per operand pair)
+constexpr int STAGES = 4;         // operand ring: a stage freed by MMA(g) must be refilled before MMA(g+3) ends
+constexpr int PCB = 32;           // channels per prep-kernel CTA
 constexpr int A_ARR = M * CB * 2; // bytes of one A operand array per stage (8 KB)
 constexpr int A_LBO = M * 16;     // bytes between 8-channel chunks of A
-constexpr int W_LOAD = 0, W_MMA = 1, W_EPI0 = 2, W_TR0 = 6, N_TR = 8, N_WARPS = 14;
+constexpr int W_LOAD = 0, W_MMA = 1, W_EPI0 = 2, N_EPI = 8, W_ZL0 = 10, W_CV0 = 14, N_ZL = 4, N_CV = 8, N_WARPS = 22;
+constexpr int ZS_MAX = 4;             // fp32 z staging ring between the z loaders and the converters (p.ZS slots)
+constexpr int Z_STAGE = CB * M * 4;   // 8 KB
 constexpr int TMEM_COLS = 512;    // two accumulator buffers of up to 256 columns
 }  // namespace tc
 
 struct TcParams {
   const float* z_p;      // [B][C][T_y]
   float* out;            // [B][T_y][T_x]
-  const unsigned char* bops;  // [B][NTL][NCB][4 arrays][4 chunks][Nt][8] bf16
-  const float* bias;     // [B][NTL*Nt]
+  const unsigned char* bops;  // [B][NTL][NCB][4 arrays][CB/8 chunks][Nt][8] bf16
+  const float* bias;     // [nsplit][B][NTL*Nt] partial sums
+  int nsplit;
   int B, C, T_y, T_x;
   int Nt;                // columns per tile, multiple of 16, <= 256
   int NTL;               // column tiles
   int MT;                // frame tiles
-  int NCB;               // channel blocks (ceil(C/32))
+  int NCB;               // channel blocks = pipeline stages per tile (ceil(C/CB))
   int tiles;             // B*MT*NTL
+  int ZS;                // z staging slots (3, or fewer when the column tile is wide)
+  int dbg;               // timing bisection only (wrong results): 1 no stores, 2 no A conversion, 4 no B copy, 8 no MMA; 16 trace
+  unsigned long long* trace;  // dbg & 16: CTA 0 appends (tag, clock) pairs
 };
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM helpers
 // ------------------------------------------------------------------------------------------------
+// debug trace (dbg & 16): CTA 0, one designated lane per role appends (tag, clock) to a shared-memory
+// log (cheap: no global traffic inside the pipeline); the log is copied out at the end of the kernel.
+constexpr int kTraceCap = 200;  // events per role
+__device__ __forceinline__ void trace_ev(const TcParams& p, unsigned long long* tsm, int* tcnt, int role, int ev, int idx) {
+  if ((p.dbg & 16) && blockIdx.x == 0) {
+    const int k = tcnt[role];
+    if (k < kTraceCap) {
+      tsm[(role * kTraceCap + k) * 2] = (static_cast<unsigned long long>(role) << 40) | (static_cast<unsigned long long>(ev) << 32) | static_cast<unsigned>(idx);
+      tsm[(role * kTraceCap + k) * 2 + 1] = clock64();
+      tcnt[role] = k + 1;
+    }
+  }
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_dst)),
                "r"(ncols)
@@ -104,6 +129,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 TMEM lanes x 16 columns: lane quad t/4 <-> frame (and frame+8), lane%4 <-> column pair; registers
+// {0,1} = frame A cols 0-7 slice, {2,3} = frame A+8, {4..7} = the same for columns 8-15.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor, canonical K-major layout without swizzle (version 1 = sm_100):
 // bits [0,14) address>>4, [16,30) leading byte offset>>4 (between the two 8-element K chunks),
 // [32,46) stride byte offset>>4 (between 8-row groups), [46,48) version, [61,64) layout type 0.
@@ -118,13 +152,18 @@ __host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo_elem, __nv_bfloat16 hi_elem) {
-  return static_cast<uint32_t>(__bfloat16_as_ushort(lo_elem)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi_elem)) << 16);
+// x = hi + lo with hi, lo bf16, using integer rounding (round-half-up on the dropped 16 bits) instead
+// of F2F conversions, which issue at a quarter of the ALU rate and were the A producers' bottleneck.
+// Returns hi in the upper and lo in the lower 16 bits of the two outputs' high halves:
+//   hi_bits, lo_bits are fp32 bit patterns whose low 16 bits are zero.
+__device__ __forceinline__ void split_bits(float x, uint32_t& hi_bits, uint32_t& lo_bits) {
+  hi_bits = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+  const float lo = x - __uint_as_float(hi_bits);  // exact
+  lo_bits = (__float_as_uint(lo) + 0x8000u) & 0xFFFF0000u;
 }
-// x = hi + lo with hi, lo bf16
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// two bf16 (given as fp32 bit patterns with zero low halves) -> one 32-bit word, first element low
+__device__ __forceinline__ uint32_t pack2(uint32_t first_bits, uint32_t second_bits) {
+  return __byte_perm(first_bits, second_bits, 0x7632);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -134,68 +173,75 @@ struct PrepParams {
   const float* m_p;     // [B][C][T_x]
   const float* logs_p;  // [B][C][T_x]
   unsigned char* bops;
-  float* bias;
-  int C, T_x, Nt, NTL, NCB;
+  float* bias;   // [nsplit][B][NTL*Nt] partial sums over the split's channels
+  int B, C, T_x, Nt, NTL, NCB;
 };
 
+// One CTA per (utterance, column tile, 32-channel block).  Thread = (8-channel chunk q, 4 consecutive
+// columns): 16 vector loads in flight, then four 16-byte groups per operand array.  The per-column
+// bias partial of the CTA's 32 channels goes to bias[pb]; the GEMM epilogue sums the partials.
 __global__ void __launch_bounds__(256) neg_cent_prep_kernel(const PrepParams p) {
-  const int cb = blockIdx.x, nt = blockIdx.y, b = blockIdx.z;
+  __shared__ float sred[4][256];
+  const int nt = blockIdx.x, b = blockIdx.y, pb = blockIdx.z;
   const int tid = threadIdx.x;
   ptx::pdl_launch_dependents();  // the GEMM kernel's A producers do not depend on us
   const float* mb = p.m_p + static_cast<size_t>(b) * p.C * p.T_x;
   const float* lb = p.logs_p + static_cast<size_t>(b) * p.C * p.T_x;
   const int n0 = nt * p.Nt;
-  unsigned char* dst = p.bops + ((static_cast<size_t>(b) * p.NTL + nt) * p.NCB + cb) * (static_cast<size_t>(p.Nt) * 256);
-  const size_t arr = static_cast<size_t>(p.Nt) * 64;  // bytes of one operand array (4 chunks x Nt x 16 B)
-  // item = (chunk q of 8 channels, column n): one 16-byte group of 8 bf16 per operand array
-  for (int item = tid; item < 4 * p.Nt; item += blockDim.x) {
-    const int q = item / p.Nt, n = item - q * p.Nt;
-    const int s = n0 + n;
-    uint32_t ivh[4], ivl[4], mvh[4], mvl[4];
+  const int nquad = p.Nt >> 2;         // Nt is a multiple of 16
+  const int q = tid / nquad;           // chunk of 8 channels inside the block (blockDim = 4 * nquad)
+  const int n = (tid - q * nquad) * 4; // first of this thread's 4 columns
+  const int s0 = n0 + n;
+  const int d0 = pb * tc::PCB + q * 8;
+  const int sb = d0 / tc::CB, chunk = (d0 % tc::CB) / 8;  // pipeline stage block and 8-channel chunk inside it
+  const size_t arr = static_cast<size_t>(p.Nt) * (tc::CB / 8) * 16;  // bytes of one operand array of a stage block
+  unsigned char* dst0 = p.bops + ((static_cast<size_t>(b) * p.NTL + nt) * p.NCB + sb) * (4 * arr);
+  const float kHalfLog2Pi = 0.91893853320467274178f;
+  const bool vec = ((p.T_x & 3) == 0) && (s0 + 3 < p.T_x) &&
+                   ((reinterpret_cast<uintptr_t>(mb) | reinterpret_cast<uintptr_t>(lb)) & 15u) == 0;
+  float l[8][4], m[8][4];
 #pragma unroll
-    for (int i2 = 0; i2 < 4; ++i2) {
-      __nv_bfloat16 h[2][4];  // [elem][iv_hi, iv_lo, mv_hi, mv_lo]
+  for (int i = 0; i < 8; ++i) {
+    const int d = d0 + i;
+    if (d < p.C && vec) {
+      const float4 lv = *reinterpret_cast<const float4*>(lb + static_cast<size_t>(d) * p.T_x + s0);
+      const float4 mv = *reinterpret_cast<const float4*>(mb + static_cast<size_t>(d) * p.T_x + s0);
+      l[i][0] = lv.x; l[i][1] = lv.y; l[i][2] = lv.z; l[i][3] = lv.w;
+      m[i][0] = mv.x; m[i][1] = mv.y; m[i][2] = mv.z; m[i][3] = mv.w;
+    } else {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int d = cb * tc::CB + q * 8 + i2 * 2 + e;
-        float iv = 0.0f, mv = 0.0f;
-        if (d < p.C && s < p.T_x) {
-          const float l = lb[static_cast<size_t>(d) * p.T_x + s];
-          const float m = mb[static_cast<size_t>(d) * p.T_x + s];
-          iv = expf(-2.0f * l);  // :223
-          mv = m * iv;           // :229
-        }
-        split_bf16(iv, h[e][0], h[e][1]);
-        split_bf16(mv, h[e][2], h[e][3]);
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = d < p.C && s0 + j < p.T_x;
+        l[i][j] = ok ? lb[static_cast<size_t>(d) * p.T_x + s0 + j] : 0.0f;
+        m[i][j] = ok ? mb[static_cast<size_t>(d) * p.T_x + s0 + j] : 0.0f;
       }
-      ivh[i2] = pack_bf16(h[0][0], h[1][0]);
-      ivl[i2] = pack_bf16(h[0][1], h[1][1]);
-      mvh[i2] = pack_bf16(h[0][2], h[1][2]);
-      mvl[i2] = pack_bf16(h[0][3], h[1][3]);
-    }
-    const size_t off = (static_cast<size_t>(q) * p.Nt + n) * 16;
-    *reinterpret_cast<uint4*>(dst + 0 * arr + off) = make_uint4(ivh[0], ivh[1], ivh[2], ivh[3]);
-    *reinterpret_cast<uint4*>(dst + 1 * arr + off) = make_uint4(ivl[0], ivl[1], ivl[2], ivl[3]);
-    *reinterpret_cast<uint4*>(dst + 2 * arr + off) = make_uint4(mvh[0], mvh[1], mvh[2], mvh[3]);
-    *reinterpret_cast<uint4*>(dst + 3 * arr + off) = make_uint4(mvl[0], mvl[1], mvl[2], mvl[3]);
-  }
-  if (cb == 0) {
-    // bias[s] = sum_d(-0.5 log 2pi - logs) + sum_d(-0.5 m^2 exp(-2 logs))     (:225, :231)
-    const float kHalfLog2Pi = 0.91893853320467274178f;
-    for (int n = tid; n < p.Nt; n += blockDim.x) {
-      const int s = n0 + n;
-      float t1 = 0.0f, t4 = 0.0f;
-      if (s < p.T_x) {
-        for (int d = 0; d < p.C; ++d) {
-          const float l = lb[static_cast<size_t>(d) * p.T_x + s];
-          const float m = mb[static_cast<size_t>(d) * p.T_x + s];
-          t1 += -kHalfLog2Pi - l;
-          t4 += (-0.5f * (m * m)) * expf(-2.0f * l);
-        }
-      }
-      p.bias[(static_cast<size_t>(b) * p.NTL + nt) * p.Nt + n] = t1 + t4;
     }
   }
+  float bias[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t ivh[8], ivl[8], mvh[8], mvl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = d0 + i < p.C && s0 + j < p.T_x;
+      const float iv = ok ? __expf(-2.0f * l[i][j]) : 0.0f;  // :223 (ex2.approx: ~2 ulp, far inside the 1e-5 bar)
+      const float mv = m[i][j] * iv;                          // :229
+      if (ok) bias[j] += (-kHalfLog2Pi - l[i][j]) + (-0.5f * (m[i][j] * m[i][j])) * iv;  // :225, :231
+      split_bits(iv, ivh[i], ivl[i]);
+      split_bits(mv, mvh[i], mvl[i]);
+    }
+    unsigned char* dst = dst0 + (static_cast<size_t>(chunk) * p.Nt + n + j) * 16;
+    *reinterpret_cast<uint4*>(dst + 0 * arr) = make_uint4(pack2(ivh[0], ivh[1]), pack2(ivh[2], ivh[3]), pack2(ivh[4], ivh[5]), pack2(ivh[6], ivh[7]));
+    *reinterpret_cast<uint4*>(dst + 1 * arr) = make_uint4(pack2(ivl[0], ivl[1]), pack2(ivl[2], ivl[3]), pack2(ivl[4], ivl[5]), pack2(ivl[6], ivl[7]));
+    *reinterpret_cast<uint4*>(dst + 2 * arr) = make_uint4(pack2(mvh[0], mvh[1]), pack2(mvh[2], mvh[3]), pack2(mvh[4], mvh[5]), pack2(mvh[6], mvh[7]));
+    *reinterpret_cast<uint4*>(dst + 3 * arr) = make_uint4(pack2(mvl[0], mvl[1]), pack2(mvl[2], mvl[3]), pack2(mvl[4], mvl[5]), pack2(mvl[6], mvl[7]));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sred[q][n + j] = bias[j];
+  __syncthreads();
+  if (tid < p.Nt)
+    p.bias[((static_cast<size_t>(pb) * p.B + b) * p.NTL + nt) * p.Nt + tid] =
+        (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,28 +253,37 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int Nt = p.Nt;
-  const uint32_t b_arr = static_cast<uint32_t>(Nt) * 64u;       // bytes of one B operand array per stage
+  const uint32_t b_arr = static_cast<uint32_t>(Nt) * (tc::CB / 8) * 16u;  // bytes of one B operand array per stage
   const uint32_t b_lbo = static_cast<uint32_t>(Nt) * 16u;       // bytes between 8-channel chunks of B
   const uint32_t stage_bytes = 4u * tc::A_ARR + 4u * b_arr;
 
   // smem: [stage][A a2_hi | a2_lo | z_hi | z_lo | B iv_hi | iv_lo | mv_hi | mv_lo] ... barriers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tc::STAGES * stage_bytes);
-  uint64_t* a_full = bars;            // [STAGES] count N_TR
-  uint64_t* b_full = bars + 2;        // [STAGES] count 1 + tx
-  uint64_t* empty = bars + 4;         // [STAGES] count 1 (tcgen05.commit)
-  uint64_t* t_full = bars + 6;        // [2] count 1 (tcgen05.commit)
-  uint64_t* t_empty = bars + 8;       // [2] count 4 (epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* zstage = reinterpret_cast<float*>(smem + tc::STAGES * stage_bytes);  // [ZS][CB][M] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tc::STAGES * stage_bytes + p.ZS * tc::Z_STAGE);
+  uint64_t* full = bars;                         // [STAGES] count N_CV (A converters) + 1 (B loader) + B bytes
+  uint64_t* empty = full + tc::STAGES;           // [STAGES] count 1 (tcgen05.commit)
+  uint64_t* t_full = empty + tc::STAGES;         // [2] count 1 (tcgen05.commit)
+  uint64_t* t_empty = t_full + 2;                // [2] count 4 (epilogue warps)
+  uint64_t* z_full = t_empty + 2;                // [ZS_MAX] count N_ZL
+  uint64_t* z_empty = z_full + tc::ZS_MAX;       // [ZS_MAX] count N_CV
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + tc::ZS_MAX);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
+  unsigned long long* tsm = reinterpret_cast<unsigned long long*>(sbias + 512);  // debug trace log (dbg & 16 only)
+  int* tcnt = reinterpret_cast<int*>(tsm + 4 * kTraceCap * 2);
+  if ((p.dbg & 16) && tid < 4) tcnt[tid] = 0;
 
   if (tid == 0) {
     for (int s = 0; s < tc::STAGES; ++s) {
-      ptx::mbar_init(&a_full[s], tc::N_TR);
-      ptx::mbar_init(&b_full[s], 1);
+      ptx::mbar_init(&full[s], tc::N_CV + 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&t_full[i], 1);
-      ptx::mbar_init(&t_empty[i], 4);
+      ptx::mbar_init(&t_empty[i], tc::N_EPI);
+    }
+    for (int i = 0; i < tc::ZS_MAX; ++i) {
+      ptx::mbar_init(&z_full[i], tc::N_ZL * 32);  // one asynchronous arrival per loader thread
+      ptx::mbar_init(&z_empty[i], tc::N_CV);
     }
     ptx::mbar_fence_init();
   }
@@ -250,13 +305,18 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
         const int tile = blockIdx.x + lt * gridDim.x;
         const int nt = tile % p.NTL;
         const int b = tile / (p.NTL * p.MT);
-        const unsigned char* src = p.bops + (static_cast<size_t>(b) * p.NTL + nt) * p.NCB * (static_cast<size_t>(Nt) * 256);
+        const unsigned char* src = p.bops + (static_cast<size_t>(b) * p.NTL + nt) * p.NCB * (4 * static_cast<size_t>(b_arr));
         for (int cb = 0; cb < p.NCB; ++cb, ++it) {
-          const int s = it & 1;
-          if (it >= 2) ptx::mbar_wait(&empty[s], ((it >> 1) - 1) & 1);
-          ptx::mbar_arrive_expect_tx(&b_full[s], 4u * b_arr);
-          ptx::bulk_g2s(smem + s * stage_bytes + 4u * tc::A_ARR, src + static_cast<size_t>(cb) * Nt * 256, 4u * b_arr,
-                        &b_full[s]);
+          const int s = it % tc::STAGES;
+          if (it >= tc::STAGES) ptx::mbar_wait(&empty[s], ((it / tc::STAGES) - 1) & 1);
+          trace_ev(p, tsm, tcnt, 0, 1, it);
+          if (p.dbg & 4) {
+            ptx::mbar_arrive(&full[s]);
+            continue;
+          }
+          ptx::mbar_arrive_expect_tx(&full[s], 4u * b_arr);
+          ptx::bulk_g2s(smem + s * stage_bytes + 4u * tc::A_ARR, src + static_cast<size_t>(cb) * (4 * static_cast<size_t>(b_arr)), 4u * b_arr,
+                        &full[s]);
         }
       }
     }
@@ -264,41 +324,63 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = instr_desc(tc::M, Nt);
+      // Base descriptors of the 4 A and 4 B operand arrays in stage 0; a stage only shifts the 14-bit
+      // address field (smem < 256 KB, so the add never carries out of it).  Building descriptors inside
+      // the loop cost ~300 cycles per stage of single-thread integer work with the tensor pipe idle.
+      uint64_t adesc[4], bdesc[4];
+      {
+        const uint32_t a0 = ptx::smem_u32(smem);
+        const uint32_t b0 = a0 + 4u * tc::A_ARR;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          adesc[i] = smem_desc(a0 + i * tc::A_ARR, tc::A_LBO, 128);
+          bdesc[i] = smem_desc(b0 + i * b_arr, b_lbo, 128);
+        }
+      }
+      const uint32_t stage_step = stage_bytes >> 4;  // descriptor address units
       uint32_t it = 0;
+      int s = 0;
+      uint32_t par = 0;
       for (int lt = 0; lt < ntile_local; ++lt) {
         const int buf = lt & 1;
         if (lt >= 2) ptx::mbar_wait(&t_empty[buf], ((lt >> 1) - 1) & 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
         for (int cb = 0; cb < p.NCB; ++cb, ++it) {
-          const int s = it & 1;
-          const uint32_t par = (it >> 1) & 1;
-          ptx::mbar_wait(&a_full[s], par);
-          ptx::mbar_wait(&b_full[s], par);
+          trace_ev(p, tsm, tcnt, 1, 0, it);
+          // test_wait first: ~10x cheaper than try_wait when the phase already completed (the usual case:
+          // the producers run ahead), and the tensor pipe only queues about one MMA, so every cycle this
+          // thread spends between two issues is an idle tensor core
+          if (!ptx::mbar_test(&full[s], par)) ptx::mbar_wait(&full[s], par);
+          trace_ev(p, tsm, tcnt, 1, 2, it);
           tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(smem + s * stage_bytes);
-          const uint32_t b0 = a0 + 4u * tc::A_ARR;
-          // operand pairs: (a2_hi,iv_hi) (a2_hi,iv_lo) (a2_lo,iv_hi) (z_hi,mv_hi) (z_hi,mv_lo) (z_lo,mv_hi)
-          const int ai[6] = {0, 0, 1, 2, 2, 3};
-          const int bi[6] = {0, 1, 0, 2, 3, 2};
-#pragma unroll
-          for (int pr = 0; pr < 6; ++pr) {
-#pragma unroll
-            for (int ks = 0; ks < tc::CB / 16; ++ks) {
-              const uint64_t ad = smem_desc(a0 + ai[pr] * tc::A_ARR + ks * 2 * tc::A_LBO, tc::A_LBO, 128);
-              const uint64_t bd = smem_desc(b0 + bi[pr] * b_arr + ks * 2 * b_lbo, b_lbo, 128);
-              umma_bf16(d_tmem, ad, bd, idesc, (cb | pr | ks) != 0 ? 1u : 0u);
-            }
+          const uint64_t soff = static_cast<uint64_t>(static_cast<uint32_t>(s) * stage_step);
+          if (!(p.dbg & 8)) {
+            // operand pairs: (a2_hi,iv_hi) (a2_hi,iv_lo) (a2_lo,iv_hi) (z_hi,mv_hi) (z_hi,mv_lo) (z_lo,mv_hi)
+            umma_bf16(d_tmem, adesc[0] + soff, bdesc[0] + soff, idesc, cb != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc[0] + soff, bdesc[1] + soff, idesc, 1u);
+            umma_bf16(d_tmem, adesc[1] + soff, bdesc[0] + soff, idesc, 1u);
+            umma_bf16(d_tmem, adesc[2] + soff, bdesc[2] + soff, idesc, 1u);
+            umma_bf16(d_tmem, adesc[2] + soff, bdesc[3] + soff, idesc, 1u);
+            umma_bf16(d_tmem, adesc[3] + soff, bdesc[2] + soff, idesc, 1u);
           }
           umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+          trace_ev(p, tsm, tcnt, 1, 3, it);
+          if (++s == tc::STAGES) {
+            s = 0;
+            par ^= 1u;
+          }
         }
         umma_commit(&t_full[buf]);  // accumulator complete
       }
     }
-  } else if (warp >= tc::W_EPI0 && warp < tc::W_TR0) {
+  } else if (warp >= tc::W_EPI0 && warp < tc::W_ZL0) {
     // ---------------- epilogue: TMEM -> registers -> (+bias) -> global ----------------
+    // tcgen05.ld shape 16x256b: a quad of lanes holds 8 consecutive fp32 columns (one 32-byte sector)
+    // of one frame, so every global store instruction writes whole sectors exactly once.
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    const int m = quarter * 32 + lane;
+    const int eh = (warp - tc::W_EPI0) >> 2;  // two warps share a lane quarter: even / odd column groups
+    const int cq = 2 * (lane & 3);  // this lane's column pair inside each group of 8
     ptx::pdl_wait();  // bias comes from the prep kernel
     for (int lt = 0; lt < ntile_local; ++lt) {
       const int tile = blockIdx.x + lt * gridDim.x;
@@ -306,90 +388,192 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       const int mt = (tile / p.NTL) % p.MT;
       const int b = tile / (p.NTL * p.MT);
       const int buf = lt & 1;
-      ptx::mbar_wait(&t_full[buf], (lt >> 1) & 1);
-      tc_fence_after();
-      const int t = mt * tc::M + m;
       const int n0 = nt * Nt;
-      const float* bias = p.bias + (static_cast<size_t>(b) * p.NTL + nt) * Nt;
-      float* orow = p.out + (static_cast<size_t>(b) * p.T_y + t) * p.T_x + n0;
-      const bool vec_ok = (p.T_x & 3) == 0;
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf) * 256u + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int c = 0; c < Nt; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        if (t < p.T_y) {
+      // bias of this tile's columns -> shared memory (sum of the prep kernel's per-channel-block partials),
+      // fetched before we wait for the accumulator so its latency hides behind the MMAs
+      {
+        float* sb = sbias + buf * 256;
+        const int e = (warp - tc::W_EPI0) * 32 + lane;
+        for (int c = e; c < Nt; c += tc::N_EPI * 32) {
+          float v = 0.0f;
+          for (int sp = 0; sp < p.nsplit; ++sp)
+            v += p.bias[((static_cast<size_t>(sp) * p.B + b) * p.NTL + nt) * Nt + c];
+          sb[c] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(tc::N_EPI * 32) : "memory");  // the epilogue warps only
+      }
+      if (warp == tc::W_EPI0 && lane == 0) trace_ev(p, tsm, tcnt, 2, 0, lt);
+      ptx::mbar_wait(&t_full[buf], (lt >> 1) & 1);
+      if (warp == tc::W_EPI0 && lane == 0) trace_ev(p, tsm, tcnt, 2, 1, lt);
+      tc_fence_after();
+      const float* bias = sbias + buf * 256;
+      const bool pair_ok = (p.T_x & 1) == 0;
+      const int ngroups = Nt >> 4;  // 16 columns per tcgen05.ld
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int mrow = quarter * 32 + h * 16 + (lane >> 2);  // this lane's first frame; the second is +8
+        const int tA = mt * tc::M + mrow, tB = tA + 8;
+        float* rowA = p.out + (static_cast<size_t>(b) * p.T_y + tA) * p.T_x + n0;
+        float* rowB = rowA + static_cast<size_t>(8) * p.T_x;
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf) * 256u + (static_cast<uint32_t>(quarter * 32 + h * 16) << 16);
+        // (+bias) and store one group of 16 columns held in registers
+        auto emit = [&](int g, const uint32_t (&cur)[8]) {
+          if (p.dbg & 1) return;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bq = *reinterpret_cast<const float4*>(bias + c + 4 * q);
-            float4 o;
-            o.x = __uint_as_float(r[4 * q + 0]) + bq.x;
-            o.y = __uint_as_float(r[4 * q + 1]) + bq.y;
-            o.z = __uint_as_float(r[4 * q + 2]) + bq.z;
-            o.w = __uint_as_float(r[4 * q + 3]) + bq.w;
-            const int n = n0 + c + 4 * q;
-            if (vec_ok && n + 3 < p.T_x) {
-              *reinterpret_cast<float4*>(orow + c + 4 * q) = o;
+          for (int i = 0; i < 2; ++i) {
+            const int c = g * 16 + i * 8 + cq;
+            const float2 bq = *reinterpret_cast<const float2*>(bias + c);
+            const float2 oA = make_float2(__uint_as_float(cur[4 * i + 0]) + bq.x, __uint_as_float(cur[4 * i + 1]) + bq.y);
+            const float2 oB = make_float2(__uint_as_float(cur[4 * i + 2]) + bq.x, __uint_as_float(cur[4 * i + 3]) + bq.y);
+            const int n = n0 + c;
+            if (pair_ok && n + 1 < p.T_x) {
+              if (tA < p.T_y) *reinterpret_cast<float2*>(rowA + c) = oA;
+              if (tB < p.T_y) *reinterpret_cast<float2*>(rowB + c) = oB;
             } else {
-              if (n + 0 < p.T_x) orow[c + 4 * q + 0] = o.x;
-              if (n + 1 < p.T_x) orow[c + 4 * q + 1] = o.y;
-              if (n + 2 < p.T_x) orow[c + 4 * q + 2] = o.z;
-              if (n + 3 < p.T_x) orow[c + 4 * q + 3] = o.w;
+              if (tA < p.T_y && n < p.T_x) rowA[c] = oA.x;
+              if (tA < p.T_y && n + 1 < p.T_x) rowA[c + 1] = oA.y;
+              if (tB < p.T_y && n < p.T_x) rowB[c] = oB.x;
+              if (tB < p.T_y && n + 1 < p.T_x) rowB[c + 1] = oB.y;
             }
           }
+        };
+        // two register sets, statically named: the load of group g+1 is in flight while group g is stored
+        uint32_t ra[8], rb[8];
+        if (eh < ngroups) {
+          tmem_ld_16x256b_x2(taddr + eh * 16, ra);
+          tmem_wait_ld();
+        }
+        for (int g = eh; g < ngroups; g += 4) {
+          if (g + 2 < ngroups) tmem_ld_16x256b_x2(taddr + (g + 2) * 16, rb);
+          emit(g, ra);
+          tmem_wait_ld();
+          if (g + 2 >= ngroups) break;
+          if (g + 4 < ngroups) tmem_ld_16x256b_x2(taddr + (g + 4) * 16, ra);
+          emit(g + 2, rb);
+          tmem_wait_ld();
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == tc::W_EPI0 && lane == 0) trace_ev(p, tsm, tcnt, 2, 2, lt);
       if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
     }
-  } else if (warp >= tc::W_TR0) {
-    // ---------------- A producers: z_p -> (-0.5 z^2, z) -> bf16 hi/lo operand tiles ----------------
-    const int tt = tid - tc::W_TR0 * 32;  // 0..255
-    const int m = tt & (tc::M - 1);
-    const int half = tt >> 7;             // which 16 of the stage's 32 channels
-    uint32_t it = 0;
-    for (int lt = 0; lt < ntile_local; ++lt) {
-      const int tile = blockIdx.x + lt * gridDim.x;
+  } else if (warp >= tc::W_ZL0 && warp < tc::W_CV0) {
+    // ---------------- z loaders: z_p (global, coalesced along frames) -> fp32 staging ring ----------------
+    // cp.async (LDGSTS) straight into shared memory: no registers, no blocking -- a loader thread only
+    // waits for a free staging slot, so ZS stages of HBM latency are in flight per SM (with register
+    // staging only ~16 KB/SM were in flight and the whole pipeline paced at the HBM round trip).
+    // Kept apart from the converters on purpose: the converters must execute fence.proxy.async, and that
+    // fence waits for every outstanding memory operation of its thread.
+    const int lt_id = tid - tc::W_ZL0 * 32;  // 0..127
+    const int G = ntile_local * p.NCB;       // stages this CTA runs
+    const size_t zstride = static_cast<size_t>(p.T_y);
+    const bool vec16 = ((p.T_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.z_p) & 15u) == 0);
+    // 16-byte mode: thread = (4 consecutive frames, channel lt_id/32 + 4k); 4-byte mode: thread = frame lt_id
+    const int fm = vec16 ? (lt_id & 31) * 4 : lt_id;
+    const int ch0 = vec16 ? (lt_id >> 5) : 0;
+    int ld_lt = 0, ld_cb = 0, zs = 0, use = 0;
+    const float* ld_ptr = nullptr;
+    int t_rem = 0;  // frames of this thread that exist (vec16: 0..4, else 0..1)
+    auto ld_new_tile = [&]() {
+      const int tile = blockIdx.x + ld_lt * gridDim.x;
       const int mt = (tile / p.NTL) % p.MT;
       const int b = tile / (p.NTL * p.MT);
-      const int t = mt * tc::M + m;
-      const bool t_ok = t < p.T_y;
-      const float* zb = p.z_p + static_cast<size_t>(b) * p.C * p.T_y + t;
-      for (int cb = 0; cb < p.NCB; ++cb, ++it) {
-        const int s = it & 1;
-        float z[16];
-        const int d0 = cb * tc::CB + half * 16;
+      const int t = mt * tc::M + fm;
+      t_rem = max(0, min(vec16 ? 4 : 1, p.T_y - t));
+      ld_ptr = p.z_p + static_cast<size_t>(b) * p.C * p.T_y + (t_rem > 0 ? t : 0);
+    };
+    ld_new_tile();
+    for (int g = 0; g < G; ++g) {
+      if (use >= 1) ptx::mbar_wait(&z_empty[zs], (use - 1) & 1);  // converters finished reading the slot
+      float* dst = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + fm;
+      const int d0 = ld_cb * tc::CB;
+      if (vec16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = (t_ok && d0 + i < p.C) ? zb[static_cast<size_t>(d0 + i) * p.T_y] : 0.0f;
-        if (it >= 2) ptx::mbar_wait(&empty[s], ((it >> 1) - 1) & 1);  // MMAs of the previous use are done
-        unsigned char* a_base = smem + s * stage_bytes;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t a2h[4], a2l[4], zh[4], zl[4];
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) {
-            __nv_bfloat16 h[2][4];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float zz = z[q * 8 + i2 * 2 + e];
-              const float a2 = -0.5f * (zz * zz);  // :227
-              split_bf16(a2, h[e][0], h[e][1]);
-              split_bf16(zz, h[e][2], h[e][3]);
-            }
-            a2h[i2] = pack_bf16(h[0][0], h[1][0]);
-            a2l[i2] = pack_bf16(h[0][1], h[1][1]);
-            zh[i2] = pack_bf16(h[0][2], h[1][2]);
-            zl[i2] = pack_bf16(h[0][3], h[1][3]);
-          }
-          const uint32_t off = static_cast<uint32_t>(half * 2 + q) * tc::A_LBO + static_cast<uint32_t>(m) * 16u;
-          *reinterpret_cast<uint4*>(a_base + 0 * tc::A_ARR + off) = make_uint4(a2h[0], a2h[1], a2h[2], a2h[3]);
-          *reinterpret_cast<uint4*>(a_base + 1 * tc::A_ARR + off) = make_uint4(a2l[0], a2l[1], a2l[2], a2l[3]);
-          *reinterpret_cast<uint4*>(a_base + 2 * tc::A_ARR + off) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
-          *reinterpret_cast<uint4*>(a_base + 3 * tc::A_ARR + off) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+        for (int k = 0; k < tc::CB / 4; ++k) {
+          const int ch = ch0 + 4 * k;
+          const int nbytes = (d0 + ch < p.C) ? t_rem * 4 : 0;  // bytes beyond are zero-filled
+          const float* src = ld_ptr + static_cast<size_t>(d0 + ch < p.C ? d0 + ch : 0) * zstride;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst + ch * tc::M)), "l"(src),
+                       "r"(nbytes)
+                       : "memory");
         }
-        fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_full[s]);
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < tc::CB; ++ch) {
+          const int nbytes = (d0 + ch < p.C) ? t_rem * 4 : 0;
+          const float* src = ld_ptr + static_cast<size_t>(d0 + ch < p.C ? d0 + ch : 0) * zstride;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(ptx::smem_u32(dst + ch * tc::M)), "l"(src),
+                       "r"(nbytes)
+                       : "memory");
+        }
+      }
+      // arrive on z_full[zs] when this thread's copies have landed (does not block the thread)
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&z_full[zs])) : "memory");
+      if (++zs == p.ZS) {
+        zs = 0;
+        ++use;
+      }
+      if (++ld_cb == p.NCB) {
+        ld_cb = 0;
+        ++ld_lt;
+        if (g + 1 < G) ld_new_tile();
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");  // nothing may still be writing our shared memory at exit
+  } else if (warp >= tc::W_CV0) {
+    // ---------------- converters: staging -> (-0.5 z^2, z) -> bf16 hi/lo operand tiles ----------------
+    const int ct = tid - tc::W_CV0 * 32;   // 0..255
+    const int m = ct & (tc::M - 1);        // frame inside the tile
+    const int half = ct >> 7;              // which 8-channel chunk of the stage's 16 channels
+    const int G = ntile_local * p.NCB;
+    int zs = 0, zuse = 0;
+    for (int g = 0; g < G; ++g) {
+      const uint32_t it = static_cast<uint32_t>(g);
+      const int s = it % tc::STAGES;
+      if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 0, g);
+      ptx::mbar_wait(&z_full[zs], zuse & 1);
+      const float* src = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + static_cast<size_t>(half * 8) * tc::M + m;
+      float z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = src[i * tc::M];
+      if (it >= tc::STAGES) ptx::mbar_wait(&empty[s], ((it / tc::STAGES) - 1) & 1);  // MMAs of the previous use are done
+      if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 1, g);
+      unsigned char* a_base = smem + s * stage_bytes;
+      if (!(p.dbg & 2)) {
+        const int q = 0;
+        uint32_t a2h[4], a2l[4], zh[4], zl[4];
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          uint32_t h[2][4];  // [elem][a2_hi, a2_lo, z_hi, z_lo] as fp32 bit patterns
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float zz = z[q * 8 + i2 * 2 + e];
+            const float a2 = -0.5f * (zz * zz);  // :227
+            split_bits(a2, h[e][0], h[e][1]);
+            split_bits(zz, h[e][2], h[e][3]);
+          }
+          a2h[i2] = pack2(h[0][0], h[1][0]);
+          a2l[i2] = pack2(h[0][1], h[1][1]);
+          zh[i2] = pack2(h[0][2], h[1][2]);
+          zl[i2] = pack2(h[0][3], h[1][3]);
+        }
+        const uint32_t off = static_cast<uint32_t>(half) * tc::A_LBO + static_cast<uint32_t>(m) * 16u;
+        *reinterpret_cast<uint4*>(a_base + 0 * tc::A_ARR + off) = make_uint4(a2h[0], a2h[1], a2h[2], a2h[3]);
+        *reinterpret_cast<uint4*>(a_base + 1 * tc::A_ARR + off) = make_uint4(a2l[0], a2l[1], a2l[2], a2l[3]);
+        *reinterpret_cast<uint4*>(a_base + 2 * tc::A_ARR + off) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+        *reinterpret_cast<uint4*>(a_base + 3 * tc::A_ARR + off) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+      }
+      fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 2, g);
+      if (lane == 0) {
+        ptx::mbar_arrive(&full[s]);
+        ptx::mbar_arrive(&z_empty[zs]);  // the staging slot was fully read (values are in registers)
+      }
+      if (++zs == p.ZS) {
+        zs = 0;
+        ++zuse;
       }
     }
   }
@@ -400,13 +584,22 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     tc_fence_after();
     tmem_dealloc(tmem_base, tc::TMEM_COLS);
   }
+  if ((p.dbg & 16) && blockIdx.x == 0 && tid == 0) {
+    unsigned long long n = 0;
+    for (int r = 0; r < 4; ++r)
+      for (int k = 0; k < tcnt[r]; ++k, ++n) {
+        p.trace[2 + 2 * n] = tsm[(r * kTraceCap + k) * 2];
+        p.trace[3 + 2 * n] = tsm[(r * kTraceCap + k) * 2 + 1];
+      }
+    p.trace[0] = n;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 struct TcShape {
-  int Nt, NTL, MT, NCB;
+  int Nt, NTL, MT, NCB, NPB;
   size_t bops_bytes, bias_bytes, total;
 };
 
@@ -416,9 +609,10 @@ static TcShape tc_shape(int B, int C, int T_y, int T_x) {
   const int per = (T_x + s.NTL - 1) / s.NTL;
   s.Nt = ((per + 15) / 16) * 16;
   s.MT = (T_y + tc::M - 1) / tc::M;
-  s.NCB = (C + tc::CB - 1) / tc::CB;
-  s.bops_bytes = static_cast<size_t>(B) * s.NTL * s.NCB * s.Nt * 256;
-  s.bias_bytes = static_cast<size_t>(B) * s.NTL * s.Nt * 4;
+  s.NCB = ((C + tc::PCB - 1) / tc::PCB) * (tc::PCB / tc::CB);  // padded to whole prep blocks (zeros beyond C)
+  s.NPB = (C + tc::PCB - 1) / tc::PCB;
+  s.bops_bytes = static_cast<size_t>(B) * s.NTL * (static_cast<size_t>(s.NPB) * tc::PCB / tc::CB) * s.Nt * (8 * tc::CB);
+  s.bias_bytes = static_cast<size_t>(s.NPB) * B * s.NTL * s.Nt * 4;  // one partial per prep block
   s.total = ((s.bops_bytes + 255) & ~size_t(255)) + ((s.bias_bytes + 255) & ~size_t(255));
   return s;
 }
@@ -433,22 +627,35 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   unsigned char* bops = static_cast<unsigned char*>(scratch);
   float* bias = reinterpret_cast<float*>(bops + ((s.bops_bytes + 255) & ~size_t(255)));
 
-  PrepParams pp{m_p, logs_p, bops, bias, C, T_x, s.Nt, s.NTL, s.NCB};
-  neg_cent_prep_kernel<<<dim3(s.NCB, s.NTL, B), 256, 0, st>>>(pp);
+  PrepParams pp{m_p, logs_p, bops, bias, B, C, T_x, s.Nt, s.NTL, s.NCB};
+  neg_cent_prep_kernel<<<dim3(s.NTL, B, s.NPB), s.Nt, 0, st>>>(pp);  // 4 chunks x Nt/4 column quads
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
 
   TcParams tp{};
-  tp.z_p = z_p; tp.out = out; tp.bops = bops; tp.bias = bias;
+  tp.z_p = z_p; tp.out = out; tp.bops = bops; tp.bias = bias; tp.nsplit = s.NPB;
   tp.B = B; tp.C = C; tp.T_y = T_y; tp.T_x = T_x;
   tp.Nt = s.Nt; tp.NTL = s.NTL; tp.MT = s.MT; tp.NCB = s.NCB;
   tp.tiles = B * s.MT * s.NTL;
-  const size_t smem = static_cast<size_t>(tc::STAGES) * (4 * tc::A_ARR + 4 * static_cast<size_t>(s.Nt) * 64) + 128;
+  {
+    const char* d = getenv("MAS_NC_DEBUG");
+    tp.dbg = d ? atoi(d) : 0;
+  }
+  static unsigned long long* d_trace = nullptr;
+  if (tp.dbg & 16) {
+    if (!d_trace) cudaMalloc(&d_trace, (2 + 2 * 4000) * 8);
+    cudaMemsetAsync(d_trace, 0, (2 + 2 * 4000) * 8, st);
+    tp.trace = d_trace;
+  }
+  const size_t fixed = static_cast<size_t>(tc::STAGES) * (4 * tc::A_ARR + 4 * static_cast<size_t>(s.Nt) * (tc::CB / 8) * 16) + 512 + 2 * 256 * 4 + 128;
+  tp.ZS = tc::ZS_MAX;
+  while (tp.ZS > 1 && fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE > 225 * 1024) --tp.ZS;
+  const size_t smem = fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE + ((tp.dbg & 16) ? (4 * 200 * 16 + 64) : 0);
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
-    e = cudaFuncSetAttribute(neg_cent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(neg_cent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -469,6 +676,17 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   e = cudaLaunchKernelEx(&cfg, neg_cent_tc_kernel, tp);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
+  if ((tp.dbg & 16) && getenv("MAS_NC_TRACE_DUMP")) {  // debug only: synchronises and prints CTA 0's event trace
+    cudaStreamSynchronize(st);
+    static unsigned long long h[2 + 2 * 4000];
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    const unsigned long long n = h[0] < 4000 ? h[0] : 4000;
+    unsigned long long t0 = ~0ull;
+    for (unsigned long long i = 0; i < n; ++i) t0 = h[3 + 2 * i] < t0 ? h[3 + 2 * i] : t0;
+    for (unsigned long long i = 0; i < n; ++i)
+      printf("TRACE role %llu ev %llu idx %llu t %llu\n", h[2 + 2 * i] >> 40, (h[2 + 2 * i] >> 32) & 0xff,
+             h[2 + 2 * i] & 0xffffffffull, h[3 + 2 * i] - t0);
+  }
   return MAS_OK;
 }
 
