@@ -130,6 +130,8 @@ void mas_set_tuning2(int fused, int helpers);
 /* Debug timeline: device pointer to 8 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
  * kernels update with min start / max end %globaltimer stamps; NULL disables. */
 void mas_set_timeline(void* dev_ptr);
+/* Debug event trace of the forward kernel's CTA 0: device pointer to 8*512*2 uint64 (zeroed), or NULL. */
+void mas_set_trace(void* dev_ptr);
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,7 @@ def test_random_sweep_bit_exact(mp, oracle, shape):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("K", [1, 2, 4, 8])
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 6, 8])
 @pytest.mark.parametrize("R", [8, 16, 32])
 def test_every_kernel_configuration(mp, oracle, K, R):
     """Each cols-per-lane / rows-per-stage instantiation, vector and scalar load paths."""

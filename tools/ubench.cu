@@ -79,6 +79,77 @@ __global__ void k_row(float* out, long long* cyc, int n, const float* __restrict
   if (threadIdx.x == 0) cyc[0] = (t1 - t0);
 }
 
+// (c2) the same recurrence with the real kernel's data movement added step by step (K = 2):
+//   MODE bit0: c values come from shared memory, loaded one 8-frame block ahead (float2 per row)
+//   MODE bit1: lane 31 stores its last column to shared memory every frame (hand-off publish)
+//   MODE bit2: lane 0's left edge comes from a shared-memory array (two float4 per block)
+//   MODE bit3: decision bits flushed to shared memory every 32 frames
+// nwarps warps run independent copies (SM-level contention of the MIO/LSU path).
+template <int MODE>
+__global__ void k_row2(float* out, long long* cyc, int nblk, const float* __restrict__ cg) {
+  constexpr int K = 2;
+  extern __shared__ __align__(16) float sm2[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* rows = sm2 + warp * (64 * 64 + 256 + 64);  // 64 frames x 64 floats
+  float* edges = rows + 64 * 64;                    // 256 floats
+  float* sink = edges + 256;
+  for (int i = lane; i < 64 * 64; i += 32) rows[i] = cg[i & 63] * 0.001f;
+  for (int i = lane; i < 256; i += 32) edges[i] = -1e9f;
+  __syncwarp();
+  float v[K];
+  uint32_t acc[K];
+  for (int j = 0; j < K; ++j) { v[j] = lane + j; acc[j] = 0; }
+  const bool lane0 = lane == 0, lane31 = lane == 31;
+  float cc[2][8][K], e[2][8];
+  auto load_block = [&](int blk, float (&c)[8][K], float (&ee)[8]) {
+    const float* rp = rows + (blk & 7) * 8 * 64 + lane * K;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MODE & 1) {
+        const float2 t = *reinterpret_cast<const float2*>(rp + i * 64);
+        c[i][0] = t.x; c[i][1] = t.y;
+      } else {
+        c[i][0] = 0.25f; c[i][1] = 0.5f;
+      }
+    }
+    if (MODE & 4) {
+      const float4 a = *reinterpret_cast<const float4*>(edges + (blk & 31) * 8);
+      const float4 b4 = *reinterpret_cast<const float4*>(edges + (blk & 31) * 8 + 4);
+      ee[0] = a.x; ee[1] = a.y; ee[2] = a.z; ee[3] = a.w; ee[4] = b4.x; ee[5] = b4.y; ee[6] = b4.z; ee[7] = b4.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ee[i] = -1e9f;
+    }
+  };
+  load_block(0, cc[0], e[0]);
+  long long t0 = clk();
+#pragma unroll 1
+  for (int blk = 0; blk < nblk; blk += 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      load_block(blk + h + 1, cc[(h + 1) & 1], e[(h + 1) & 1]);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float left = __shfl_up_sync(0xffffffffu, v[K - 1], 1);
+        if (lane0) left = e[h][r];
+        const float d1 = v[1] - v[0];
+        acc[1] = __funnelshift_l(__float_as_uint(d1), acc[1], 1);
+        v[1] = cc[h][r][1] + fmaxf(v[0], v[1]);
+        const float d0 = v[0] - left;
+        acc[0] = __funnelshift_l(__float_as_uint(d0), acc[0], 1);
+        v[0] = cc[h][r][0] + fmaxf(left, v[0]);
+        if ((MODE & 2) && lane31) sink[(h * 8 + r) & 63] = v[K - 1];
+      }
+      if ((MODE & 8) && (((blk + h) & 3) == 3)) {
+        *reinterpret_cast<uint2*>(rows + 63 * 64 + lane * 2) = make_uint2(acc[0], acc[1]);
+      }
+    }
+  }
+  long long t1 = clk();
+  out[threadIdx.x] = v[0] + v[1] + acc[0] + acc[1];
+  if (lane == 0) cyc[warp] = (t1 - t0);
+}
+
 // (d) mbarrier try_wait on an already completed phase; LDS latency; arrive cost
 __global__ void k_mbar(long long* cyc, int n) {
   __shared__ uint64_t bar;
@@ -175,6 +246,18 @@ int main() {
     if (rep) printf("row recurrence K=%d: %.1f cycles per row (1 warp, registers only)\n", K, h[0] / (8.0 * n)); \
   }
   ROW(1) ROW(2) ROW(3) ROW(4) ROW(6) ROW(8)
+  {
+    const int nblk = 1024;
+    const size_t smem2 = 4 * (64 * 64 + 256 + 64) * sizeof(float);
+#define ROW2(MODE, NW)                                                                         \
+    CK(cudaFuncSetAttribute(k_row2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    for (int rep = 0; rep < 2; ++rep) {                                                        \
+      k_row2<MODE><<<1, 32 * NW, smem2>>>(out, cyc, nblk, c);                                  \
+      CK(cudaMemcpy(h, cyc, 8 * NW, cudaMemcpyDeviceToHost));                                  \
+      if (rep) printf("row K=2 mode %2d warps %d: %.1f cycles/row\n", MODE, NW, h[0] / (8.0 * nblk)); \
+    }
+    ROW2(0, 1) ROW2(1, 1) ROW2(2, 1) ROW2(4, 1) ROW2(8, 1) ROW2(3, 1) ROW2(7, 1) ROW2(15, 1) ROW2(15, 3) ROW2(15, 4) ROW2(0, 3)
+  }
   for (int rep = 0; rep < 2; ++rep) {
     k_mbar<<<1, 32>>>(cyc, n);
     CK(cudaMemcpy(h, cyc, 24, cudaMemcpyDeviceToHost));
@@ -189,7 +272,7 @@ int main() {
   CK(cudaMemset(src, 1, per_cta * 148));
   CK(cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   int chunks[] = {768, 3072, 6144, 12288, 24576, 49152};
-  for (int ctas : {1, 64, 148}) {
+  for (int ctas : {64}) {
     for (int chunk : chunks) {
       for (int S : {2, 4, 8}) {
         if (static_cast<size_t>(S) * chunk > 190 * 1024) continue;

@@ -180,5 +180,6 @@ void mas_set_neg_cent_impl(int impl) { mas::set_neg_cent_impl(impl); }
 void mas_set_debug_kernels(int mask) { mas::set_debug_kernels(mask); }
 void mas_set_tuning2(int fused, int helpers) { mas::set_tuning2(fused, helpers); }
 void mas_set_timeline(void* dev_ptr) { mas::set_timeline(static_cast<unsigned long long*>(dev_ptr)); }
+void mas_set_trace(void* dev_ptr) { mas::set_trace(static_cast<unsigned long long*>(dev_ptr)); }
 
 }  // extern "C"

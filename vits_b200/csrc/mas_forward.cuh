@@ -34,6 +34,27 @@ __device__ __forceinline__ double mask_at(const void* p, int dtype, int64_t off)
   }
 }
 
+// strided sum of n mask elements starting at `base` (element stride `stride`), dtype resolved once so
+// the loads of one thread are independent and overlap
+template <typename T>
+__device__ __forceinline__ double mask_sum_t(const T* base, int64_t stride, int n, int tid, int nthr) {
+  double s = 0.0;
+#pragma unroll 4
+  for (int i = tid; i < n; i += nthr) s += static_cast<double>(static_cast<float>(base[i * stride]));
+  return s;
+}
+__device__ __forceinline__ double mask_sum(const void* p, int dtype, int64_t off, int64_t stride, int n, int tid, int nthr) {
+  switch (dtype) {
+    case MAS_F32: return mask_sum_t(static_cast<const float*>(p) + off, stride, n, tid, nthr);
+    case MAS_U8: return mask_sum_t(static_cast<const uint8_t*>(p) + off, stride, n, tid, nthr);
+    default: {
+      double s = 0.0;
+      for (int i = tid; i < n; i += nthr) s += mask_at(p, dtype, off + i * stride);
+      return s;
+    }
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -57,9 +78,11 @@ struct FwdParams {
   int64_t msb, msy, msx;
   int32_t* lens;    // [B][2] = (t_y, t_x), (0,0) when invalid
   int32_t* status;  // sticky MAS_STATUS_* bits
+  int32_t* wo_counters;  // the write-out kernel's two work counters; zeroed here before it may start
   uint32_t* bits;   // [B][G][TXP]   (unfused mode only)
   int32_t* index;   // [B][T_y]      (fused mode: written by this kernel)
   unsigned long long* tl;  // optional timeline stamps (debug), or nullptr
+  unsigned long long* trace;  // optional per-warp event trace of CTA 0 (debug): [8 warps][512][2]
   int B, T_y, T_x;
   int S;            // ring stages
   int W;            // DP warps covering the padded T_x
@@ -68,6 +91,7 @@ struct FwdParams {
   int G;            // ceil(T_y/32)
   int BR;           // hand-off ring length in frames (power of two >= (S+1)*R)
   int fused;        // 1: decision bits stay in shared memory and this kernel also backtracks
+  int pdl;          // launch with the programmatic-serialization attribute
   uint32_t slot_bytes;
   FwdSmem sm;
 };
@@ -141,6 +165,17 @@ __device__ __forceinline__ void load_row(float (&c)[K], const float* __restrict_
       const float2 t = *reinterpret_cast<const float2*>(row + xl);
       c[0] = t.x;
       c[1] = t.y;
+    } else if (K == 3) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) c[j] = row[min(xl + j, T_x - 1)];
+    } else if (K == 6) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        // T_x is even on this path: a pair is entirely inside or entirely outside the row
+        const float2 t = *reinterpret_cast<const float2*>(row + min(xl + 2 * q, T_x - 2));
+        c[2 * q + 0] = t.x;
+        c[2 * q + 1] = t.y;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < K / 4; ++q) {
@@ -202,8 +237,36 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
 
   // Let the dependent kernels (backtrack, write-out) get scheduled right away: the write-out's
   // zero-fill does not depend on us.
+  // This kernel may itself have been launched programmatically (behind the previous call's write-out):
+  // everything above touched only shared memory; global memory is first used below.
+  ptx::pdl_wait();
+  if (b == 0 && tid == 0) {
+    p.wo_counters[0] = 0;
+    p.wo_counters[1] = 0;
+    __threadfence();
+  }
+  __syncthreads();  // the counters are zero before any thread of this kernel lets the write-out start
   ptx::pdl_launch_dependents();
   if (tid == 0) tl_min(p.tl, 0);
+
+  // The first ring stages are requested before the lengths are known (they only need T_y as a bound;
+  // frames beyond t_y are padding that exists in memory), so the HBM latency of the first frames
+  // overlaps the mask reduction.
+  const float* nc_b = p.nc + static_cast<size_t>(b) * p.T_y * p.T_x;
+  const uint32_t lead_bytes = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(nc_b) & 15u);
+  const int nspec = min(S, (p.T_y + R - 1) / R);
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::mbar_fence_init();
+    const unsigned char* src0 = reinterpret_cast<const unsigned char*>(nc_b) - lead_bytes;
+    for (int c = 0; c < nspec; ++c) {
+      const int rows = min(R, p.T_y - c * R);
+      const uint32_t bytes = (lead_bytes + static_cast<uint32_t>(rows) * p.T_x * 4u + 15u) & ~15u;
+      ptx::mbar_arrive_expect_tx(&full[c], bytes);
+      ptx::bulk_g2s(reinterpret_cast<unsigned char*>(ring) + static_cast<size_t>(c) * p.slot_bytes,
+                    src0 + static_cast<size_t>(c) * R * p.T_x * 4u, bytes, &full[c]);
+    }
+  }
 
   // ---- lengths -------------------------------------------------------------------------------
   if (p.t_ys != nullptr) {
@@ -214,8 +277,8 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   } else {
     double sy = 0.0, sx = 0.0;
     const int64_t base = static_cast<int64_t>(b) * p.msb;
-    for (int y = tid; y < p.T_y; y += blockDim.x) sy += mask_at(p.mask, p.mask_dtype, base + y * p.msy);
-    for (int x = tid; x < p.T_x; x += blockDim.x) sx += mask_at(p.mask, p.mask_dtype, base + x * p.msx);
+    sy = mask_sum(p.mask, p.mask_dtype, base, p.msy, p.T_y, tid, blockDim.x);
+    sx = mask_sum(p.mask, p.mask_dtype, base, p.msx, p.T_x, tid, blockDim.x);
     sy = warp_sum(sy);
     sx = warp_sum(sx);
     if (lane == 0) {
@@ -245,6 +308,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
         atomicOr(p.status, st);
         p.lens[2 * b] = 0;
         p.lens[2 * b + 1] = 0;
+        for (int c = 0; c < nspec; ++c) ptx::mbar_wait(&full[c], 0);  // no copy may outlive the CTA
       }
       if (fused)
         for (int y = tid; y < p.T_y; y += blockDim.x) p.index[static_cast<size_t>(b) * p.T_y + y] = -1;
@@ -256,10 +320,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   if (tid == 0) {
     p.lens[2 * b] = t_y;
     p.lens[2 * b + 1] = t_x;
-    for (int s = 0; s < S; ++s) {
-      ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], W_act);
-    }
+    for (int s = 0; s < S; ++s) ptx::mbar_init(&empty[s], W_act);
     for (int i = 0; i < (W - 1) * S; ++i) ptx::mbar_init(&bfull[i], 1);
     if (fused)
       for (int g = 0; g <= g_top; ++g) ptx::mbar_init(&gbar[g], W_act);
@@ -272,8 +333,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   if (tid >= 1 && tid <= W) bnd[static_cast<size_t>(tid) * BR] = kNeg;
   __syncthreads();
 
-  const float* nc_b = p.nc + static_cast<size_t>(b) * p.T_y * p.T_x;
-  const uint32_t lead_bytes = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(nc_b) & 15u);
   const size_t slot_floats = p.slot_bytes / 4;
   const int dw = warp - 1;
 
@@ -282,10 +341,13 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
     if (lane == 0) {
       const int nchunks = (t_y + R - 1) / R;
       const unsigned char* src0 = reinterpret_cast<const unsigned char*>(nc_b) - lead_bytes;
-      int s = 0;
-      uint32_t par = 1;  // parity of the previous use of the stage
-      for (int c = 0; c < nchunks; ++c) {
-        if (c >= S) ptx::mbar_wait(&empty[s], par);
+      // stages 0..nspec-1 were requested in the prologue; speculative ones beyond the utterance's
+      // frames are never consumed, so drain them here (no copy may outlive the CTA)
+      for (int c = nchunks; c < nspec; ++c) ptx::mbar_wait(&full[c], 0);
+      int s = nspec % S;
+      uint32_t par = (nspec == S) ? 0u : 1u;  // parity of the previous use of the stage
+      for (int c = nspec; c < nchunks; ++c) {
+        ptx::mbar_wait(&empty[s], par);
         const int rows = min(R, t_y - c * R);
         const uint32_t bytes = (lead_bytes + static_cast<uint32_t>(rows) * p.T_x * 4u + 15u) & ~15u;
         ptx::mbar_arrive_expect_tx(&full[s], bytes);
@@ -304,7 +366,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
     // bnd[dw+1].  bnd[0] is constant (the x==0 sentinel), bnd[W_act] is a sink nobody reads, so the
     // inner loop is identical (and branch-free) for every warp.
     const int x0 = (dw * 32 + lane) * K;
-    const int xl = (VEC && K < 4) ? min(x0, p.T_x - K) : x0;  // load column (padding lanes are clamped)
+    const int xl = (VEC && K < 3) ? min(x0, p.T_x - K) : x0;  // load column (padding lanes are clamped)
     const bool has_left = dw > 0;
     const bool has_right = dw < W_act - 1;
     const float* bnd_in = bnd + static_cast<size_t>(dw) * BR;
@@ -323,6 +385,19 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
       v[j] = kNeg;
       acc[j] = 0u;
     }
+#ifdef MAS_TRACE  // compile-time only: even a never-taken runtime check costs the DP warps ~3 us per call
+    int tr_n = 0;  // debug trace cursor (CTA 0, lane 0 of each DP warp; plain stores, no atomics)
+    auto tr = [&](int tag, int idx) {
+      if (p.trace && b == 0 && lane0 && tr_n < 512) {
+        unsigned long long* q = p.trace + (static_cast<size_t>(dw) * 512 + tr_n) * 2;
+        q[0] = (static_cast<unsigned long long>(tag) << 32) | static_cast<unsigned>(idx);
+        q[1] = clock64();
+        ++tr_n;
+      }
+    };
+#else
+    auto tr = [](int, int) {};
+#endif
 
     auto flush_bits = [&](int g, int nrows) {
       uint32_t* dst = bits_b + static_cast<size_t>(g) * p.TXP;
@@ -355,55 +430,95 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
     };
 
     // ---- main loop: one ring stage (R frames) per iteration, straight-line inside ------------
+    // The first block of the NEXT stage is prefetched during the last block of the current one when
+    // that stage happens to be ready (non-blocking test only: a warp must never block on a stage
+    // while it still holds one, that dead-locks once S <= W); its shared-memory latency and the
+    // barrier checks then hide behind the recurrence instead of sitting between two stages.
     int stage = 0;
     uint32_t par = 0u;
     const int nfull = t_y / R;  // R is a compile-time power of two
     int y0 = 0;
+    constexpr bool XPF = (BPC % 2) == 0;  // buffer 0 is free while the last (odd) block runs
+    float cc[2][8][K], e[2][8];
+    bool have0 = false;  // block 0 of the current stage is already in cc[0]/e[0]
     for (int c = 0; c < nfull; ++c, y0 += R) {
-      // test_wait first: it is ~3x cheaper than try_wait when the phase has already completed
-      if (!ptx::mbar_test(&full[stage], par)) ptx::mbar_wait(&full[stage], par);            // frames landed
-      if (has_left && !ptx::mbar_test(&bfull[(dw - 1) * S + stage], par))
-        ptx::mbar_wait(&bfull[(dw - 1) * S + stage], par);                                  // left neighbour done
       const float* rp = ring + static_cast<size_t>(stage) * slot_floats + (lead_bytes >> 2);
       const int sl = y0 & (BR - 1);  // BR is a multiple of R: no wrap inside the stage
       const float* ep = bnd_in + sl;
+      tr(1, c);
+      if (!have0) {
+        // test_wait first: it is ~3x cheaper than try_wait when the phase has already completed
+        if (!ptx::mbar_test(&full[stage], par)) ptx::mbar_wait(&full[stage], par);            // frames landed
+        tr(2, c);
+        if (has_left && !ptx::mbar_test(&bfull[(dw - 1) * S + stage], par))
+          ptx::mbar_wait(&bfull[(dw - 1) * S + stage], par);                                  // left neighbour done
+        tr(3, c);
+        load_block(rp, ep, cc[0], e[0]);
+      }
       float* bo = bnd_out + sl;
       float* bo_last = bnd_out + ((y0 + R) & (BR - 1));
       const bool diag_stage = (y0 + R > xw0) && (y0 < xw1);  // warp-uniform
       const int dx = x0 - y0;                                 // column - frame at the stage's first frame
+      // position of the next stage, for the cross-stage prefetch
+      int nstage = stage + 1;
+      uint32_t npar = par;
+      if (nstage == S) {
+        nstage = 0;
+        npar ^= 1u;
+      }
+      bool next_ready = false;
 
       // the whole stage is straight-line code; the diagonal variant is chosen once per stage
-      auto stage_body = [&](auto diag_tag) {
+      auto stage_body = [&](auto diag_tag, auto mod_tag) {
         constexpr bool DIAG = decltype(diag_tag)::value;
-        float cc[2][8][K], e[2][8];
-        load_block(rp, ep, cc[0], e[0]);
+        constexpr int Y0MOD = decltype(mod_tag)::value;  // y0 % K (0 whenever K divides the stage length)
 #pragma unroll
         for (int kb = 0; kb < BPC; ++kb) {
-          if (kb + 1 < BPC)
+          if (kb + 1 < BPC) {
             load_block(rp + static_cast<size_t>(kb + 1) * 8 * T_x, ep + (kb + 1) * 8, cc[(kb + 1) & 1],
                        e[(kb + 1) & 1]);
+          } else if (XPF && c + 1 < nfull) {
+            bool ok = ptx::mbar_test(&full[nstage], npar);
+            if (has_left) ok = ok && ptx::mbar_test(&bfull[(dw - 1) * S + nstage], npar);
+            next_ready = __all_sync(0xffffffffu, ok);
+            if (next_ready)
+              load_block(ring + static_cast<size_t>(nstage) * slot_floats + (lead_bytes >> 2),
+                         bnd_in + ((y0 + R) & (BR - 1)), cc[0], e[0]);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int r = kb * 8 + i, jd = r % K;  // K divides 8 and y0: only column r % K can be diagonal
+            const int r = kb * 8 + i, jd = (Y0MOD + r) % K;  // only column (y0 + r) % K of a lane can be diagonal
             row_step<K, DIAG>(v, acc, cc[kb & 1][i], e[kb & 1][i], lane0, jd, DIAG && (dx + jd == r));
             if (lane31) *(r < R - 1 ? bo + r + 1 : bo_last) = v[K - 1];
           }
         }
       };
-      if (diag_stage)
-        stage_body(std::true_type{});
-      else
-        stage_body(std::false_type{});
+      if (!diag_stage) {
+        stage_body(std::false_type{}, std::integral_constant<int, 0>{});
+      } else if (R % K == 0) {
+        stage_body(std::true_type{}, std::integral_constant<int, 0>{});
+      } else {  // K in {3, 6}: y0 % K cycles through the multiples of gcd(R, K)
+        switch (y0 % K) {
+          case 0: stage_body(std::true_type{}, std::integral_constant<int, 0>{}); break;
+          case 1: stage_body(std::true_type{}, std::integral_constant<int, 1 % K>{}); break;
+          case 2: stage_body(std::true_type{}, std::integral_constant<int, 2 % K>{}); break;
+          case 3: stage_body(std::true_type{}, std::integral_constant<int, 3 % K>{}); break;
+          case 4: stage_body(std::true_type{}, std::integral_constant<int, 4 % K>{}); break;
+          default: stage_body(std::true_type{}, std::integral_constant<int, 5 % K>{}); break;
+        }
+      }
+      have0 = next_ready;
+      tr(4, c);
 
       if (c == 0 && dw == 0 && lane0) bnd[0] = kNeg;  // the (0,0) special case is consumed
       if (((y0 + R) & 31) == 0) flush_bits(y0 >> 5, 32);
+      tr(5, c);
       __syncwarp();
       if (lane0) ptx::mbar_arrive(&empty[stage]);                               // stage may be refilled
       if (lane31 && has_right) ptx::mbar_arrive(&bfull[dw * S + stage]);       // our last column is published
-      if (++stage == S) {
-        stage = 0;
-        par ^= 1u;
-      }
+      tr(6, c);
+      stage = nstage;
+      par = npar;
     }
     // ---- < R leftover frames, one at a time ------------------------------------------------------
     if (y0 < t_y) {
@@ -496,8 +611,17 @@ inline cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<p.B, 32 * (1 + p.W + p.H), p.sm.total, st>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.B);
+  cfg.blockDim = dim3(32 * (1 + p.W + p.H));
+  cfg.dynamicSmemBytes = p.sm.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <int K, bool VEC, bool BIG>
@@ -519,7 +643,9 @@ inline cudaError_t launch_fwd(const FwdParams& p, int R, cudaStream_t st) {
 // one entry per K, defined in mas_fwd_k{1,2,4,8}.cu
 cudaError_t launch_fwd_k1(bool vec, const FwdParams& p, int R, cudaStream_t st);
 cudaError_t launch_fwd_k2(bool vec, const FwdParams& p, int R, cudaStream_t st);
+cudaError_t launch_fwd_k3(bool vec, const FwdParams& p, int R, cudaStream_t st);
 cudaError_t launch_fwd_k4(bool vec, const FwdParams& p, int R, cudaStream_t st);
+cudaError_t launch_fwd_k6(bool vec, const FwdParams& p, int R, cudaStream_t st);
 cudaError_t launch_fwd_k8(bool vec, const FwdParams& p, int R, cudaStream_t st);
 
 }  // namespace mas

@@ -17,6 +17,7 @@ void set_tuning(int K, int R, int S, int pdl);
 void set_debug_kernels(int mask);
 void set_tuning2(int fused, int helpers);
 void set_timeline(unsigned long long* dev_ptr);
+void set_trace(unsigned long long* dev_ptr);
 
 // mas_neg_cent.cu
 int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,

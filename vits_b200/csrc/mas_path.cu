@@ -130,12 +130,16 @@ __global__ void __launch_bounds__(1024, 1) mas_backtrack_kernel(const BtParams p
 struct WoParams {
   unsigned char* out;    // [B*T_y][T_x] elements of es bytes
   const int32_t* index;  // [B*T_y]
+  int32_t* counters;     // [0] next zero-fill chunk to claim, [1] chunks finished (zeroed by the forward kernel)
   long long rows;        // B*T_y
+  long long bytes;       // rows * T_x * es
+  int nchunks;           // zero-fill chunks of kWoChunk bytes
   int T_x;
   int es;                // element size in bytes
   unsigned long long one;  // bit pattern of 1 in the element type
   unsigned long long* tl;
 };
+constexpr long long kWoChunk = 32 * 1024;
 
 __device__ __forceinline__ void store_elem(unsigned char* p, int es, unsigned long long bits) {
   switch (es) {
@@ -146,26 +150,36 @@ __device__ __forceinline__ void store_elem(unsigned char* p, int es, unsigned lo
   }
 }
 
+// Phase A (zero-fill) is work-stealing: whichever CTAs are resident claim 32 KiB chunks from a counter
+// until none are left, so the fill is done by the CTAs that land on SMs the forward kernel leaves idle
+// (the launch requests enough shared memory that a write-out CTA cannot share an SM with a forward
+// CTA -- its stores would slow the latency-bound DP warps) and CTAs that only become resident after
+// the forward kernel has finished find nothing left to do.  Phase B (the ones) waits for the forward /
+// backtrack kernels (griddepcontrol.wait) and for every chunk to be finished.
 __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
+  __shared__ int s_chunk;
   const int tid = threadIdx.x;
+  ptx::pdl_launch_dependents();  // the next call's forward kernel may set up while we run
   if (tid == 0) tl_min(p.tl, 5);
-  const long long per = (p.rows + gridDim.x - 1) / gridDim.x;
-  const long long r0 = min(p.rows, per * blockIdx.x);
-  const long long r1 = min(p.rows, r0 + per);
-  if (r0 < r1) {
-    // phase A: zero-fill this CTA's rows (independent of the forward/backtrack kernels)
-    unsigned char* beg = p.out + static_cast<size_t>(r0) * p.T_x * p.es;
-    unsigned char* end = p.out + static_cast<size_t>(r1) * p.T_x * p.es;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (;;) {
+    if (tid == 0) s_chunk = atomicAdd(&p.counters[0], 1);
+    __syncthreads();
+    const int c = s_chunk;
+    __syncthreads();
+    if (c >= p.nchunks) break;
+    const long long b0 = static_cast<long long>(c) * kWoChunk;
+    const long long b1 = min(p.bytes, b0 + kWoChunk);
+    unsigned char* beg = p.out + b0;
+    unsigned char* end = p.out + b1;
+    // out is aligned to its element size only: unaligned head/tail bytes go element-wise
     unsigned char* abeg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(beg) + 15u) & ~uintptr_t(15));
     if (abeg > end) abeg = end;
     unsigned char* aend = abeg + ((end - abeg) & ~ptrdiff_t(15));
-    for (unsigned char* q = beg + static_cast<size_t>(tid) * p.es; q < abeg; q += static_cast<size_t>(blockDim.x) * p.es)
-      store_elem(q, p.es, 0ull);
-    for (unsigned char* q = aend + static_cast<size_t>(tid) * p.es; q < end; q += static_cast<size_t>(blockDim.x) * p.es)
-      store_elem(q, p.es, 0ull);
+    for (unsigned char* q = beg + tid; q < abeg; q += blockDim.x) *q = 0;
+    for (unsigned char* q = aend + tid; q < end; q += blockDim.x) *q = 0;
     uint4* a4 = reinterpret_cast<uint4*>(abeg);
     const size_t n4 = static_cast<size_t>(aend - abeg) >> 4;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     size_t i = tid;
     for (; i + 3 * blockDim.x < n4; i += 4 * blockDim.x) {
       a4[i] = z;
@@ -174,11 +188,23 @@ __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
       a4[i + 3 * blockDim.x] = z;
     }
     for (; i < n4; i += blockDim.x) a4[i] = z;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();  // release: the chunk's zeros are visible before the count
+      atomicAdd(&p.counters[1], 1);
+    }
   }
-  // phase B: the ones.  Same CTA wrote the zeros of these rows; the barrier orders them.
   if (tid == 0) tl_max(p.tl, 6);
+  // phase B: the ones
   ptx::pdl_wait();
+  if (tid == 0) {
+    while (atomicAdd(&p.counters[1], 0) < p.nchunks) __nanosleep(64);
+    __threadfence();  // acquire
+  }
   __syncthreads();
+  const long long per = (p.rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = min(p.rows, per * blockIdx.x);
+  const long long r1 = min(p.rows, r0 + per);
   for (long long r = r0 + tid; r < r1; r += blockDim.x) {
     const int x = p.index[r];
     if (x >= 0) store_elem(p.out + (static_cast<size_t>(r) * p.T_x + x) * p.es, p.es, p.one);
@@ -192,6 +218,7 @@ __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
 static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
 static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only)
 static unsigned long long* g_timeline = nullptr;
+static unsigned long long* g_trace = nullptr;
 
 struct Layout {
   int G, TXP_max;
@@ -202,7 +229,10 @@ struct Layout {
 static Layout scratch_layout(int B, int T_y, int T_x) {
   Layout L;
   L.G = (T_y + 31) / 32;
-  L.TXP_max = ((T_x + 255) / 256) * 256;  // multiple of 32*K for every K <= 8
+  // row stride of the decision words is W*32*K; take the largest over the supported K (1,2,3,4,6,8)
+  L.TXP_max = ((T_x + 255) / 256) * 256;
+  if (((T_x + 191) / 192) * 192 > L.TXP_max) L.TXP_max = ((T_x + 191) / 192) * 192;
+  if (((T_x + 95) / 96) * 96 > L.TXP_max) L.TXP_max = ((T_x + 95) / 96) * 96;
   auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
   L.off_status = 0;
   L.off_lens = 256;
@@ -246,7 +276,7 @@ static bool pick_fwd_config(int T_y, int T_x, FwdConfig* cfg) {
   if (K == 0) K = T_x <= 32 ? 1 : (T_x <= 448 ? 2 : (T_x <= 896 ? 4 : 8));
   int W = (T_x + 32 * K - 1) / (32 * K);
   while (W > 27 && K < 8) {
-    K *= 2;
+    K = (K == 3 || K == 6) ? 8 : K * 2;
     W = (T_x + 32 * K - 1) / (32 * K);
   }
   if (W > 27) return false;
@@ -285,6 +315,8 @@ static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int 
   switch (K) {
     case 1: return launch_fwd_k1(vec, p, R, st);
     case 2: return launch_fwd_k2(vec, p, R, st);
+    case 3: return launch_fwd_k3(vec, p, R, st);
+    case 6: return launch_fwd_k6(vec, p, R, st);
     case 4: return launch_fwd_k4(vec, p, R, st);
     case 8: return launch_fwd_k8(vec, p, R, st);
     default: return cudaErrorInvalidValue;
@@ -358,6 +390,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
   fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
   fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
+  fp.wo_counters = status + 4;
+  fp.pdl = g_tune_pdl;
+  fp.trace = g_trace;
   fp.B = B; fp.T_y = T_y; fp.T_x = T_x;
   fp.S = fc.S; fp.W = fc.W; fp.H = fc.H; fp.TXP = fc.W * 32 * fc.K; fp.G = L.G; fp.BR = fc.BR;
   fp.fused = fc.fused; fp.slot_bytes = fc.slot_bytes; fp.sm = fc.sm;
@@ -406,14 +441,29 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     WoParams wp{};
     wp.out = static_cast<unsigned char*>(path_out);
     wp.index = index;
+    wp.counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;
     wp.tl = g_timeline;
     wp.rows = static_cast<long long>(B) * T_y;
+    wp.bytes = wp.rows * T_x * es;
+    wp.nchunks = static_cast<int>((wp.bytes + kWoChunk - 1) / kWoChunk);
     wp.T_x = T_x;
     wp.es = es;
     wp.one = one_bits(path_dtype);
-    long long want = (wp.rows * T_x * es + (64 * 1024 - 1)) / (64 * 1024);  // >= 64 KiB per CTA
-    int grid = static_cast<int>(want < 1 ? 1 : (want > 8LL * g_num_sms ? 8LL * g_num_sms : want));
-    e = launch_pdl(mas_writeout_kernel, dim3(grid), dim3(256), 0, st, wp);
+    // few enough CTAs that all of them are resident at once on the SMs the forward kernel leaves idle
+    // (they all have to run phase B; a CTA that starts only after the forward kernel adds tail latency)
+    int grid = wp.nchunks < 2 * g_num_sms ? wp.nchunks : 2 * g_num_sms;
+    if (grid < 1) grid = 1;
+    // Dynamic shared memory the write-out does not use: just enough that its CTAs cannot be co-resident
+    // with a forward CTA; they still pack several per SM on the SMs the forward kernel leaves idle.
+    long long wo_smem = 229LL * 1024 - static_cast<long long>(fc.sm.total);
+    if (wo_smem < 0 || wo_smem > 56 * 1024) wo_smem = 0;  // forward CTA too small to exclude cheaply
+    static bool wo_attr = false;
+    if (!wo_attr) {
+      e = cudaFuncSetAttribute(mas_writeout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      wo_attr = true;
+    }
+    e = launch_pdl(mas_writeout_kernel, dim3(grid), dim3(256), static_cast<size_t>(wo_smem), st, wp);
     if (e != cudaSuccess) return static_cast<int>(e);
     count_launch();
   }
@@ -427,6 +477,7 @@ size_t maximum_path_scratch_bytes(int B, int T_y, int T_x) {
 
 void set_debug_kernels(int mask) { g_debug_kernels = mask; }
 void set_timeline(unsigned long long* dev_ptr) { g_timeline = dev_ptr; }
+void set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
 void set_tuning(int K, int R, int S, int pdl) {
   g_tune_K = K;
