@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
         return
     B, T_y, T_x = WORKLOADS[args.workload]
     rng = np.random.default_rng(1234)
-    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, args.ragged)
+    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, not args.full_length)
     import torch
     from oracle import mas_oracle
     stock = mas_oracle.load_ref_core("stock")
@@ -186,7 +186,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: B={B} T_y={T_y} T_x={T_x} {'ragged' if args.ragged else 'full-length'} "
+        "config": {"workload": f"{args.workload}: B={B} T_y<={T_y} T_x<={T_x} {'full-length' if args.full_length else 'variable lengths'} "
                                "neg_cent~N(-400,20^2), CPU tensors in and out",
                    "path": "monotonic_align.maximum_path wrapper marshalling (__init__.py:14-20) + the reference's "
                            "compiled core.pyx, built with its setup.py's flags (no OpenMP => serial prange)"},
@@ -213,96 +213,110 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     B, T_y, T_x = WORKLOADS[args.workload]
-    rng = np.random.default_rng(1234 + rank)
-    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, args.ragged)
-    ty_d = torch.as_tensor(t_ys, device=dev)
-    tx_d = torch.as_tensor(t_xs, device=dev)
-    ym = torch.arange(T_y, device=dev)[None, :] < ty_d[:, None]
-    xm = torch.arange(T_x, device=dev)[None, :] < tx_d[:, None]
-    mask = (ym[:, :, None] & xm[:, None, :]).float()          # [B,T_y,T_x] like attn_mask.squeeze(1)
 
     # rotating buffer sets so that consecutive steps never find their input or output in L2
     plane_bytes = B * T_y * T_x * 4
     nbuf = max(2, min(8, int(np.ceil(3 * 126e6 / (2 * plane_bytes)))))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ncs = [torch.randn(B, T_y, T_x, generator=g, device=dev) * 20 - 400 for _ in range(nbuf)]
-    outs = [None] * nbuf
-
-    def step(i):
-        outs[i % nbuf] = vits_b200.maximum_path(ncs[i % nbuf], mask)
-
-    # --- correctness gate before timing: oracle on rank 0's first buffer (bit-exact) ---
-    parity = None
-    if rank == 0:
-        from oracle import mas_oracle
-        want = mas_oracle.maximum_path_numpy(ncs[0].cpu().numpy(), t_ys, t_xs)
-        step(0)
-        torch.cuda.synchronize()
-        parity = bool(np.array_equal(outs[0].cpu().numpy().astype(np.int32), want))
-        assert parity, "GPU path differs from the oracle -- refusing to report a number"
-
-    # CUDA graphs remove the Python/ctypes enqueue cost from the device timeline.  One graph holds one
-    # pass over all `nbuf` rotating buffer sets (= nbuf steps, so the programmatic launch edge between a
-    # step's write-out and the next step's forward kernel is inside the graph); single-step graphs cover
-    # the remainder so that EXACTLY `steps` steps are timed.
-    graphs = None
-    multi = None
-    launches_per_step = None
-    if not args.no_graph:
-        try:
-            for i in range(nbuf):
-                step(i)
-            torch.cuda.synchronize()
-            graphs = []
-            for i in range(nbuf):
-                gr = torch.cuda.CUDAGraph()
-                n0 = _lib.launch_count()
-                with torch.cuda.graph(gr):
-                    step(i)
-                launches_per_step = _lib.launch_count() - n0
-                graphs.append(gr)
-            multi = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(multi):
-                for i in range(nbuf):
-                    step(i)
-        except Exception as e:  # pragma: no cover
-            print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
-            graphs = multi = None
-
-    def run_steps(n):
-        """Run exactly n steps."""
-        if graphs is None:
-            for i in range(n):
-                step(i)
-            return
-        for _ in range(n // nbuf):
-            multi.replay()
-        for i in range(n % nbuf):
-            graphs[i].replay()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(args.warmup)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = (_lib.launch_count() - n0) if graphs is None else launches_per_step * args.steps
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max * 1e-3)
+    def time_variant(ragged, steps, warmup, sample_clocks):
+        """One workload variant: parity gate on rank 0, graph capture, W warm-up + exactly K timed steps."""
+        rng = np.random.default_rng(1234 + rank)
+        t_ys, t_xs = make_lengths(rng, B, T_y, T_x, ragged)
+        ty_d = torch.as_tensor(t_ys, device=dev)
+        tx_d = torch.as_tensor(t_xs, device=dev)
+        ym = torch.arange(T_y, device=dev)[None, :] < ty_d[:, None]
+        xm = torch.arange(T_x, device=dev)[None, :] < tx_d[:, None]
+        mask = (ym[:, :, None] & xm[:, None, :]).float()          # [B,T_y,T_x] like attn_mask.squeeze(1)
+        outs = [None] * nbuf
+
+        def step(i):
+            outs[i % nbuf] = vits_b200.maximum_path(ncs[i % nbuf], mask)
+
+        # correctness gate before timing: oracle on rank 0's first buffer (bit-exact)
+        parity = None
+        if rank == 0:
+            from oracle import mas_oracle
+            want = mas_oracle.maximum_path_numpy(ncs[0].cpu().numpy(), t_ys, t_xs)
+            step(0)
+            torch.cuda.synchronize()
+            parity = bool(np.array_equal(outs[0].cpu().numpy().astype(np.int32), want))
+            assert parity, "GPU path differs from the oracle -- refusing to report a number"
+
+        # CUDA graphs remove the Python/ctypes enqueue cost from the device timeline.  One graph holds one
+        # pass over all `nbuf` rotating buffer sets (= nbuf steps, so the programmatic launch edge between a
+        # step's write-out and the next step's forward kernel is inside the graph); single-step graphs cover
+        # the remainder so that EXACTLY `steps` steps are timed.
+        graphs = multi = None
+        launches_per_step = None
+        if not args.no_graph:
+            try:
+                for i in range(nbuf):
+                    step(i)
+                torch.cuda.synchronize()
+                graphs = []
+                for i in range(nbuf):
+                    gr = torch.cuda.CUDAGraph()
+                    n0 = _lib.launch_count()
+                    with torch.cuda.graph(gr):
+                        step(i)
+                    launches_per_step = _lib.launch_count() - n0
+                    graphs.append(gr)
+                multi = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(multi):
+                    for i in range(nbuf):
+                        step(i)
+            except Exception as e:  # pragma: no cover
+                print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+                graphs = multi = None
+
+        def run_steps(n):
+            if graphs is None:
+                for i in range(n):
+                    step(i)
+                return
+            for _ in range(n // nbuf):
+                multi.replay()
+            for i in range(n % nbuf):
+                graphs[i].replay()
+
+        run_steps(warmup)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_steps(steps)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = (_lib.launch_count() - n0) if graphs is None else launches_per_step * steps
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        alg_bytes = 4 * int(np.sum(t_ys.astype(np.int64) * t_xs)) + 4 * B * T_y * T_x   # SURVEY.md 8(d)
+        return dict(t_ys=t_ys, t_xs=t_xs, ty_d=ty_d, tx_d=tx_d, mask=mask, ms_max=ms_max, step_ms=ms_max / steps,
+                    value=world * B * steps / (ms_max * 1e-3), clocks=clocks, launches=int(launches), parity=parity,
+                    graph=graphs is not None, alg_bytes=alg_bytes)
+
+    # primary: the BASELINE.json configuration (variable lengths with masks) unless --full-length; the other
+    # variant is timed with fewer steps and reported beside it
+    primary_ragged = not args.full_length
+    R = time_variant(primary_ragged, args.steps, args.warmup, True)
+    O = time_variant(not primary_ragged, max(20, args.steps // 4), max(3, args.warmup // 2), False)
+    t_ys, t_xs, ty_d, tx_d, mask = R["t_ys"], R["t_xs"], R["ty_d"], R["tx_d"], R["mask"]
+    ms_max, value, clocks, launches, parity = R["ms_max"], R["value"], R["clocks"], R["launches"], R["parity"]
+    graphs = True if R["graph"] else None
 
     # --- per-kernel durations: serialised pass (PDL off, eager), events between the three kernels ---
     kernels_ms = None
@@ -353,34 +367,34 @@ def run_ours(args, rank, world, local_rank):
         all_lens = torch.empty(world * B, 2, dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(all_lens, lens)
         if rank == 0:
-            gi, gl = gathered.cpu().numpy(), all_lens.cpu().numpy()
-            ok = True
-            for b in range(world * B):
-                ty, tx = int(gl[b, 0]), int(gl[b, 1])
-                row = gi[b, :ty]
-                d = np.diff(row)
-                ok &= bool(row[0] == 0 and row[-1] == tx - 1 and ((d == 0) | (d == 1)).all() and (gi[b, ty:] == -1).all())
+            gl = all_lens.cpu().numpy()
+            ok = vits_b200.shard.check_index(gathered, gl[:, 0], gl[:, 1])
             verified = ok
             assert ok, "gathered paths violate the alignment invariants"
 
     if rank == 0:
-        alg_bytes = 4 * int(np.sum(t_ys.astype(np.int64) * t_xs)) + 4 * B * T_y * T_x
+        alg_bytes = R["alg_bytes"]
         peak, peak_src = measured_peak_gbs()
-        step_ms = ms_max / args.steps
+        step_ms = R["step_ms"]
         achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+        other = {"workload": "full-length" if primary_ragged else "ragged lengths", "value": O["value"], "unit": UNIT,
+                 "ms_per_step": O["step_ms"], "steps": max(20, args.steps // 4),
+                 "roofline_frac": O["alg_bytes"] / (O["step_ms"] * 1e-3) / 1e9 / peak, "parity_checked": O["parity"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: B={B}/GPU T_y={T_y} T_x={T_x} {'ragged lengths' if args.ragged else 'full-length'}"
+            "config": {"workload": f"{args.workload}: B={B}/GPU T_y<={T_y} T_x<={T_x} "
+                                   f"{'variable lengths (SURVEY 8d: t_x~U[T_x/2,T_x], t_y~U[max(t_x,T_y/2),T_y], element 0 full)' if primary_ragged else 'full-length'}"
                                    f" with [B,T_y,T_x] fp32 mask, neg_cent~N(-400,20^2) fp32 -> fp32 path",
+                       "other_variant": other,
                        "l2": f"inputs larger than L2: {nbuf} rotating (neg_cent, path) buffer sets = "
                              f"{2 * nbuf * plane_bytes / 1e6:.0f} MB, no flush kernel in the timed region",
                        "launch": (f"CUDA graph replay, {nbuf} consecutive steps per graph (one per rotating buffer set)" if graphs is not None else "eager ctypes launches"),
                        "parity_checked": parity, "multi_gpu_verified": verified},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                         "traffic": (100.7e6 if not primary_ragged else None), "traffic_note": "full-length c2, ncu --set full: mas_forward 50.4 MB DRAM read + mas_writeout 50.3 MB written (profiles/); not captured for the variable-length variant", "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
                          "kernel": "maximum_path chain (mas_forward with fused backtrack + mas_writeout, PDL-overlapped, "
                                    "timed as one unit with CUDA events on the launching stream)",
                          "phase_timeline_us": kernels_ms},
@@ -439,7 +453,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--ragged", action="store_true", help="variable lengths (SURVEY 8d) instead of full-length")
+    ap.add_argument("--full-length", action="store_true",
+                    help="headline on the full-length variant (default: variable lengths, BASELINE.json configs[1])")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
