@@ -91,6 +91,46 @@ def test_every_kernel_configuration(mp, oracle, K, R):
     L.mas_set_tuning2(-1, 0)
 
 
+def test_more_utterances_than_sms(mp, oracle):
+    """B >= SM count: the forward CTAs run in waves, so the ones are dropped by the write-out kernel, not by
+    the forward kernel (which would wait for a zero-fill that cannot start)."""
+    rng = np.random.default_rng(123)
+    B, T_y, T_x = 333, 96, 40
+    nc = (rng.standard_normal((B, T_y, T_x)) * 2).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+    for _ in range(2):
+        np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs), want)
+
+
+def test_back_to_back_calls_share_scratch(mp, oracle):
+    """Consecutive calls overlap through programmatic dependent launch and reuse one scratch buffer:
+    enqueue many without synchronising, with and without the dense path, then check every result."""
+    rng = np.random.default_rng(77)
+    B, T_y, T_x = 6, 420, 160
+    ncs, lens, wants = [], [], []
+    for _ in range(12):
+        nc = (rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        ncs.append(torch.from_numpy(nc).cuda())
+        lens.append((torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()))
+        wants.append(oracle.maximum_path_numpy(nc, t_ys, t_xs))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        outs = []
+        for i, nc in enumerate(ncs):
+            if (i + rep) % 3 == 2:
+                outs.append(("index", mp.maximum_path_index(nc, y_lengths=lens[i][0], x_lengths=lens[i][1])))
+            else:
+                outs.append(("path", mp.maximum_path_from_lengths(nc, lens[i][0], lens[i][1])))
+        torch.cuda.synchronize()
+        for (kind, out), want in zip(outs, wants):
+            if kind == "path":
+                np.testing.assert_array_equal(out.cpu().numpy().astype(np.int32), want)
+            else:
+                np.testing.assert_array_equal(out.cpu().numpy(), path_to_index(want))
+
+
 def test_ties_and_huge_magnitudes(mp, oracle):
     rng = np.random.default_rng(11)
     nc = rng.integers(-2, 3, size=(4, 300, 150)).astype(np.float32)          # dense ties

@@ -571,12 +571,23 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   // ---- fused tail: the backtrack proper (core.pyx:30-33) ------------------------------------------
   __syncthreads();  // all decision words and exit tables are in shared memory
   if (warp == 0) {
-    // chain over groups, top to bottom: walk the top group from (t_y-1, t_x-1), then table look-ups
+    // (1) top group, whose entry (t_y-1, t_x-1) is known.  The walk can visit at most 32 columns; lane l
+    // holds the decision word of column t_x-1-l, 32 ballots transpose them into one mask per frame, and
+    // the walk itself is then pure register arithmetic (no dependent shared-memory loads).
+    const int rt = (t_y - 1) & 31;
+    const int col = t_x - 1 - lane;
+    const uint32_t w = col >= 0 ? sbits[static_cast<size_t>(g_top) * p.TXP + col] : 0u;
+    uint32_t pos = 0;
+#pragma unroll
+    for (int r = 31; r >= 0; --r) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (w >> (31 - r)) & 1u);  // bit l: decision of column t_x-1-l
+      if (r <= rt) pos += (m >> pos) & 1u;
+    }
+    // (2) chain over the groups below: one table look-up each
     if (lane == 0) {
       int cur = t_x - 1;
       sentry[g_top] = cur;
-      const uint32_t* row = sbits + static_cast<size_t>(g_top) * p.TXP;
-      for (int r = (t_y - 1) & 31; r >= 0; --r) cur = bt_step(cur, r, row[cur]);
+      cur -= static_cast<int>(pos);
       for (int g = g_top - 1; g >= 0; --g) {
         sentry[g] = cur;
         cur = sexit[static_cast<size_t>(g) * p.TXP + cur];
