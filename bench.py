@@ -320,8 +320,14 @@ def run_ours(args, rank, world, local_rank):
 
     # --- per-kernel durations: serialised pass (PDL off, eager), events between the three kernels ---
     kernels_ms = None
+    breakdown = None
     if rank == 0:
         kernels_ms = per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev)
+        if not args.no_breakdown:
+            try:
+                breakdown = contraction_and_e2e(B, T_y, T_x, t_ys, t_xs, dev)
+            except Exception as ex:  # pragma: no cover
+                breakdown = {"error": str(ex)}
 
     # --- end to end through the host-buffer C entry (pinned host memory) ---
     e2e = None
@@ -392,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
                              f"{2 * nbuf * plane_bytes / 1e6:.0f} MB, no flush kernel in the timed region",
                        "launch": (f"CUDA graph replay, {nbuf} consecutive steps per graph (one per rotating buffer set)" if graphs is not None else "eager ctypes launches"),
                        "parity_checked": parity, "multi_gpu_verified": verified},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "path_breakdown": breakdown,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (100.7e6 if not primary_ragged else None), "traffic_note": "full-length c2, ncu --set full: mas_forward 50.4 MB DRAM read + mas_writeout 50.3 MB written (profiles/); not captured for the variable-length variant", "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
                          "kernel": "maximum_path chain (mas_forward with fused backtrack + mas_writeout, PDL-overlapped, "
@@ -408,6 +414,53 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def contraction_and_e2e(B, T_y, T_x, t_ys, t_xs, dev, C=192, reps=5):
+    """neg_cent alone (ours vs the reference's fp32 torch expression, same
+    inputs, HBM-resident) and z_p,m_p,logs_p -> path end to end on the device, CUDA-graph timed."""
+    import torch
+    import vits_b200
+    from oracle import mas_oracle
+    g = torch.Generator(device=dev).manual_seed(4321)
+    nset = 3
+    sets = [(torch.randn(B, C, T_y, generator=g, device=dev), torch.randn(B, C, T_x, generator=g, device=dev),
+             torch.randn(B, C, T_x, generator=g, device=dev) * 0.3) for _ in range(nset)]
+    y_len = torch.as_tensor(t_ys, device=dev)
+    x_len = torch.as_tensor(t_xs, device=dev)
+
+    def timeit(fn):
+        for st in sets[:2]:
+            fn(*st)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            keep = [fn(*st) for st in sets]
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        del keep
+        return e0.elapsed_time(e1) / (reps * nset) * 1e3
+
+    ref = mas_oracle.neg_cent_torch(*sets[0])
+    ours = vits_b200.neg_cent(*sets[0])
+    rel = float(((ours - ref).abs().amax() / ref.abs().amax()).item())
+    t_ref = timeit(mas_oracle.neg_cent_torch)
+    t_nc = timeit(vits_b200.neg_cent)
+    t_e2e = timeit(lambda z, m, ls: vits_b200.maximum_path_from_lengths(vits_b200.neg_cent(z, m, ls), y_len, x_len))
+    flops = 4.0 * B * T_y * T_x * C
+    nbytes = 4.0 * (B * C * T_y + 2 * B * C * T_x + B * T_y * T_x)
+    return {"neg_cent_us": t_nc, "neg_cent_torch_fp32_us": t_ref, "neg_cent_rel_err_of_max": rel,
+            "neg_cent_algorithmic_gflop": flops / 1e9, "neg_cent_algorithmic_mb": nbytes / 1e6,
+            "neg_cent_gbs": nbytes / t_nc / 1e3, "neg_cent_tflops": flops / t_nc / 1e6,
+            "stats_to_path_us": t_e2e, "stats_to_path_alignments_per_s": B / t_e2e * 1e6,
+            "note": "device-resident inputs, CUDA-graph replay over 3 rotating input sets; torch = the reference's "
+                    "inline fp32 expression (SynthesizerTrn.py:223-232)"}
 
 
 def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=5):
@@ -458,6 +511,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the neg_cent / stats->path timings")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

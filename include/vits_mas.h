@@ -113,6 +113,25 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                  void* scratch, size_t scratch_bytes,
                  int B, int C, int T_y, int T_x, mas_stream_t stream);
 
+/*
+ * Callers either side of the path.  All pointers are device pointers, fp32 contiguous
+ * unless strides are given; asynchronous on `stream`.
+ *
+ * mas_path_durations -- replaces `w = attn.sum(2)` (SynthesizerTrn.py:237): w[b,x] = number of frames the
+ *   alignment gives to text position x.  index = the int32 [B,T_y] output of mas_maximum_path (-1 = padded).
+ * mas_expand_prior   -- replaces `einsum('bctn,bdn->bdt', attn, m_p)` and the same for logs_p
+ *   (SynthesizerTrn.py:247-248, 308-310, 359-360, 410-411): out[b,c,y] = src[b,c,index[b,y]], 0 on padded frames.
+ *   logs_p / logs_out may both be NULL to expand a single tensor.
+ * mas_generate_path  -- replaces commons.generate_path (commons.py:101-117): path[b,y,x] =
+ *   ((y < cum[x]) - (y < cum[x-1])) * mask[b,y,x] with cum = cumsum(duration[b,:]); mask is a [B,T_y,T_x] fp32
+ *   view with element strides (the reference's [b,1,t_y,t_x] attn_mask, squeezed).
+ */
+int mas_path_durations(const int32_t* index, float* w, int B, int T_y, int T_x, mas_stream_t stream);
+int mas_expand_prior(const int32_t* index, const float* m_p, const float* logs_p, float* m_out, float* logs_out,
+                     int B, int C, int T_y, int T_x, mas_stream_t stream);
+int mas_generate_path(const float* duration, const float* mask, int64_t mask_sb, int64_t mask_sy, int64_t mask_sx,
+                      float* path, int B, int T_y, int T_x, mas_stream_t stream);
+
 /* Number of kernel launches the library has issued since load (bench.py's gpu_launches). */
 uint64_t mas_launch_count(void);
 

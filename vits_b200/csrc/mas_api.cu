@@ -170,6 +170,20 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                        static_cast<cudaStream_t>(stream));
 }
 
+int mas_path_durations(const int32_t* index, float* w, int B, int T_y, int T_x, mas_stream_t stream) {
+  return mas::path_durations(index, w, B, T_y, T_x, static_cast<cudaStream_t>(stream));
+}
+
+int mas_expand_prior(const int32_t* index, const float* m_p, const float* logs_p, float* m_out, float* logs_out, int B,
+                     int C, int T_y, int T_x, mas_stream_t stream) {
+  return mas::expand_prior(index, m_p, logs_p, m_out, logs_out, B, C, T_y, T_x, static_cast<cudaStream_t>(stream));
+}
+
+int mas_generate_path(const float* duration, const float* mask, int64_t mask_sb, int64_t mask_sy, int64_t mask_sx,
+                      float* path, int B, int T_y, int T_x, mas_stream_t stream) {
+  return mas::generate_path(duration, mask, mask_sb, mask_sy, mask_sx, path, B, T_y, T_x, static_cast<cudaStream_t>(stream));
+}
+
 uint64_t mas_launch_count(void) { return mas::g_launches.load(std::memory_order_relaxed); }
 
 /* Tuning hooks for benchmarks (not part of the reference-facing surface). 0 = automatic. */

@@ -19,6 +19,13 @@ void set_tuning2(int fused, int helpers);
 void set_timeline(unsigned long long* dev_ptr);
 void set_trace(unsigned long long* dev_ptr);
 
+// mas_consumers.cu
+int path_durations(const int32_t* index, float* w, int B, int T_y, int T_x, cudaStream_t st);
+int expand_prior(const int32_t* index, const float* m_p, const float* logs_p, float* m_out, float* logs_out, int B, int C,
+                 int T_y, int T_x, cudaStream_t st);
+int generate_path(const float* duration, const float* mask, int64_t msb, int64_t msy, int64_t msx, float* path, int B,
+                  int T_y, int T_x, cudaStream_t st);
+
 // mas_neg_cent.cu
 int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
              int B, int C, int T_y, int T_x, cudaStream_t st);
