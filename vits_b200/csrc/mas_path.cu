@@ -273,7 +273,9 @@ static bool pick_fwd_config(int T_y, int T_x, FwdConfig* cfg) {
   const uint32_t budget = 200 * 1024;
   int K = g_tune_K;
   // keep the block small: <= 7 warps besides the producer get the full register budget
-  if (K == 0) K = T_x <= 32 ? 1 : (T_x <= 448 ? 2 : (T_x <= 896 ? 4 : 8));
+  // measured (tools/sweep.py): three DP warps of 64 columns win at T_x = 192 (39.5 vs 41.4 us), but a fourth
+  // warp costs more than wider lanes do: T_x = 256 runs 58 us with K = 4 against 78 us with K = 2
+  if (K == 0) K = T_x <= 32 ? 1 : (T_x <= 192 ? 2 : (T_x <= 896 ? 4 : 8));
   int W = (T_x + 32 * K - 1) / (32 * K);
   while (W > 27 && K < 8) {
     K = (K == 3 || K == 6) ? 8 : K * 2;
