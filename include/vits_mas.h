@@ -143,7 +143,8 @@ void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl);
 void mas_set_neg_cent_impl(int impl);
 /* Benchmark isolation: bit0 forward DP, bit1 backtrack, bit2 write-out; default 7 (all). */
 void mas_set_debug_kernels(int mask);
-/* fused: -1 automatic, 0 separate backtrack kernel, 1 backtrack fused into the forward kernel;
+/* fused: -1 automatic, 0 separate backtrack kernel after the forward kernel, 1 backtrack fused into the
+ * forward kernel, 2 streaming backtrack kernel on the idle SMs while the forward kernel runs;
  * helpers: helper warps of the fused kernel (0 = automatic). */
 void mas_set_tuning2(int fused, int helpers);
 /* Debug timeline: device pointer to 8 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the

@@ -82,13 +82,34 @@ def test_every_kernel_configuration(mp, oracle, K, R):
         nc = (rng.standard_normal(shape) * 2 - 1).astype(np.float32)
         t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
         want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
-        for stages, pdl, fused, helpers in ((2, 1, 0, 0), (5, 0, 0, 0), (3, 1, 1, 1), (4, 0, 1, 4), (0, 1, -1, 0)):
+        for stages, pdl, fused, helpers in ((2, 1, 0, 0), (5, 0, 0, 0), (3, 1, 1, 1), (4, 0, 1, 4), (0, 1, -1, 0),
+                                            (3, 1, 2, 0), (0, 0, 2, 0)):
             L.mas_set_tuning(K, R, stages, pdl)
             L.mas_set_tuning2(fused, helpers)
             got = _gpu_path(mp, nc, t_ys, t_xs)
             np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} fused={fused} {shape}")
     L.mas_set_tuning(0, 0, 0, 1)
     L.mas_set_tuning2(-1, 0)
+
+
+def test_streaming_backtrack_with_16_bit_tables(mp, oracle):
+    """Long utterances: the streaming backtrack keeps 16-bit exit columns and re-walks the groups."""
+    L = mp._lib.lib()
+    rng = np.random.default_rng(4096)
+    B, T_y, T_x = 2, 5000, 300
+    nc = (rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs)
+    try:
+        for mode in (2, -1, 0):
+            L.mas_set_tuning2(mode, 0)
+            ncd = torch.from_numpy(nc).cuda()
+            got = mp.maximum_path_from_lengths(ncd, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+            np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want, err_msg=f"mode {mode}")
+            idx = mp.maximum_path_index(ncd, y_lengths=torch.as_tensor(t_ys), x_lengths=torch.as_tensor(t_xs))
+            np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want), err_msg=f"mode {mode}")
+    finally:
+        L.mas_set_tuning2(-1, 0)
 
 
 def test_more_utterances_than_sms(mp, oracle):

@@ -79,7 +79,8 @@ struct FwdParams {
   int32_t* lens;    // [B][2] = (t_y, t_x), (0,0) when invalid
   int32_t* status;  // sticky MAS_STATUS_* bits
   int32_t* wo_counters;  // the write-out kernel's two work counters; zeroed here before it may start
-  uint32_t* bits;   // [B][G][TXP]   (unfused mode only)
+  uint32_t* bits;   // [B][G][TXP]   (unfused mode only); streaming mode: pairs {word, tag = 1}
+  uint2* lenstag;   // streaming mode: [B] {t_y << 12 | t_x, tag = 1}; else nullptr
   int32_t* index;   // [B][T_y]      (fused mode: written by this kernel)
   unsigned long long* tl;  // optional timeline stamps (debug), or nullptr
   unsigned long long* trace;  // optional per-warp event trace of CTA 0 (debug): [8 warps][512][2]
@@ -240,15 +241,6 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   // This kernel may itself have been launched programmatically (behind the previous call's write-out):
   // everything above touched only shared memory; global memory is first used below.
   ptx::pdl_wait();
-  if (b == 0 && tid == 0) {
-    p.wo_counters[0] = 0;
-    p.wo_counters[1] = 0;
-    __threadfence();
-  }
-  __syncthreads();  // the counters are zero before any thread of this kernel lets the write-out start
-  ptx::pdl_launch_dependents();
-  if (tid == 0) tl_min(p.tl, 0);
-
   // The first ring stages are requested before the lengths are known (they only need T_y as a bound;
   // frames beyond t_y are padding that exists in memory), so the HBM latency of the first frames
   // overlaps the mask reduction.
@@ -267,6 +259,28 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
                     src0 + static_cast<size_t>(c) * R * p.T_x * 4u, bytes, &full[c]);
     }
   }
+
+  if (b == 0 && tid == 0) {
+    p.wo_counters[0] = 0;
+    p.wo_counters[1] = 0;
+  }
+  const bool ll = p.lenstag != nullptr;
+  if (ll) {
+    // Streaming mode hands the decision words to the concurrently running backtrack kernel without any
+    // fence: every 32-bit word travels in one 8-byte store together with a tag, and a reader accepts an
+    // element only when the tag is set -- the flag-in-data scheme of NCCL's LL protocol (a GPU-scope
+    // release per group would cost a DP warp ~0.8 us each).  Clear this utterance's tags (whatever the
+    // scratch held: its layout depends on the shape) before the backtrack kernel can start.
+    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
+    const int n16 = p.G * p.TXP / 2;  // TXP is a multiple of 32
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) p.lenstag[b] = make_uint2(0u, 0u);
+  }
+  if (ll) __syncthreads();
+  if (tid == 0 && (ll || b == 0)) __threadfence();  // (cumulative: covers the other threads' stores ordered by the barrier)
+  __syncthreads();  // counters and tags are cleared before any thread of this CTA lets the dependent kernels start
+  ptx::pdl_launch_dependents();
+  if (tid == 0) tl_min(p.tl, 0);
 
   // ---- lengths -------------------------------------------------------------------------------
   if (p.t_ys != nullptr) {
@@ -308,6 +322,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
         atomicOr(p.status, st);
         p.lens[2 * b] = 0;
         p.lens[2 * b + 1] = 0;
+        if (ll) p.lenstag[b] = make_uint2(0u, 1u);
         for (int c = 0; c < nspec; ++c) ptx::mbar_wait(&full[c], 0);  // no copy may outlive the CTA
       }
       if (fused)
@@ -320,6 +335,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   if (tid == 0) {
     p.lens[2 * b] = t_y;
     p.lens[2 * b + 1] = t_x;
+    if (ll) p.lenstag[b] = make_uint2((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), 1u);
     for (int s = 0; s < S; ++s) ptx::mbar_init(&empty[s], W_act);
     for (int i = 0; i < (W - 1) * S; ++i) ptx::mbar_init(&bfull[i], 1);
     if (fused)
@@ -403,7 +419,17 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
       uint32_t* dst = bits_b + static_cast<size_t>(g) * p.TXP;
       const int sh = 32 - nrows;
       if (x0 == 0) acc[0] = 0u;  // the backtrack never leaves column 0 (core.pyx:32 `index != 0`)
-      if (K % 4 == 0) {
+      if (ll) {
+        uint2* d2 = reinterpret_cast<uint2*>(p.bits) + (static_cast<size_t>(b) * p.G + g) * p.TXP + x0;
+        if (K % 2 == 0) {
+#pragma unroll
+          for (int q = 0; q < K / 2; ++q)
+            *reinterpret_cast<uint4*>(d2 + 2 * q) = make_uint4(acc[2 * q] << sh, 1u, acc[2 * q + 1] << sh, 1u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < K; ++j) d2[j] = make_uint2(acc[j] << sh, 1u);
+        }
+      } else if (K % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < K / 4; ++q)
           *reinterpret_cast<uint4*>(dst + 4 * q) =

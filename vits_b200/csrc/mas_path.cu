@@ -137,6 +137,7 @@ struct WoParams {
   int T_x;
   int es;                // element size in bytes
   unsigned long long one;  // bit pattern of 1 in the element type
+  int ones;                // 1: phase B (the ones) runs here; 0: the streaming backtrack kernel drops them
   unsigned long long* tl;
 };
 constexpr long long kWoChunk = 32 * 1024;
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
     }
   }
   if (tid == 0) tl_max(p.tl, 6);
+  if (!p.ones) return;
   // phase B: the ones
   ptx::pdl_wait();
   if (tid == 0) {
@@ -213,6 +215,227 @@ __global__ void __launch_bounds__(256) mas_writeout_kernel(const WoParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 (streaming): backtrack concurrent with the forward kernel
+// ------------------------------------------------------------------------------------------------
+struct BsParams {
+  const uint2* bits;        // [B][G][TXP] {decision word, tag} written by K1
+  const uint2* lenstag;     // [B] {t_y << 12 | t_x}
+  int32_t* index;           // [B][T_y] or nullptr
+  unsigned char* path;      // [B][T_y][T_x] elements of es bytes, or nullptr
+  const int32_t* fill_counters;  // [1] = zero-fill chunks finished
+  int nchunks;
+  int T_y, T_x, TXP, G;
+  int TXS;                  // shared-memory row stride in words (odd)
+  int cols_per_warp;        // 32*K of the forward kernel: ceil(t_x / cols_per_warp) warps arrive per group
+  int dec16;                // 1: tables hold 16-bit exit columns (long utterances), the per-frame index is re-walked from the words
+  int es;
+  unsigned long long one;
+  unsigned long long* tl;
+};
+
+__device__ __forceinline__ void store_one(unsigned char* p, int es, unsigned long long bits) {
+  switch (es) {
+    case 1: *p = static_cast<unsigned char>(bits); break;
+    case 2: *reinterpret_cast<uint16_t*>(p) = static_cast<uint16_t>(bits); break;
+    case 4: *reinterpret_cast<uint32_t*>(p) = static_cast<uint32_t>(bits); break;
+    default: *reinterpret_cast<unsigned long long*>(p) = bits; break;
+  }
+}
+
+// Walk one 32-frame group from QP*32 entry columns per pass (QP independent chains per lane hide the
+// shared-memory latency) and record, per entry column, the 32 decisions taken: bit r = "stepped left
+// when leaving frame r".  The exit column is entry - popc(word); the column at frame r is
+// entry - popc(word >> (r+1)).
+template <int QP>
+__device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, uint16_t* ex, int t_x, int lane) {
+  const uint32_t row_addr = ptx::smem_u32(row);
+  for (int e0 = lane; e0 < t_x; e0 += 32 * QP) {
+    uint32_t addr[QP], dw[QP];
+#pragma unroll
+    for (int q = 0; q < QP; ++q) {
+      addr[q] = row_addr + 4u * static_cast<uint32_t>(min(e0 + 32 * q, t_x - 1));
+      dw[q] = 0u;
+    }
+#pragma unroll
+    for (int r = 31; r >= 0; --r) {
+#pragma unroll
+      for (int q = 0; q < QP; ++q) {
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr[q]));
+        const uint32_t bit = (w >> (31 - r)) & 1u;
+        dw[q] = dw[q] * 2u + bit;  // ends with the decision of frame r in bit r
+        addr[q] -= 4u * bit;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < QP; ++q)
+      if (e0 + 32 * q < t_x) {
+        if (dec) dec[e0 + 32 * q] = dw[q];
+        else ex[e0 + 32 * q] = static_cast<uint16_t>(e0 + 32 * q - __popc(dw[q]));
+      }
+  }
+}
+
+__global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nw = blockDim.x >> 5;
+  uint32_t* sdec = reinterpret_cast<uint32_t*>(smem);                       // [G][TXS] walk decisions, or ...
+  uint16_t* sexit = reinterpret_cast<uint16_t*>(smem);                      // ... [G][TXS] exit columns (dec16)
+  uint32_t* sstage = sdec + ((static_cast<size_t>(p.G) * p.TXS) >> (p.dec16 ? 1 : 0)) + 1;  // [nw][TXS] a group's words
+  int* sentry = reinterpret_cast<int*>(sstage + static_cast<size_t>(nw) * p.TXS);  // [G]
+  int* smisc = sentry + p.G;                                                // [4]: t_y, t_x, entry below the top group, tag
+
+  ptx::pdl_launch_dependents();  // the next call's forward kernel may set up while we run
+  if (tid == 0) tl_min(p.tl, 3);
+  if (tid == 0) {
+    uint2 lt;
+    while ((lt = __ldcg(p.lenstag + b)).y != 1u) __nanosleep(100);
+    smisc[0] = static_cast<int>(lt.x >> 12);
+    smisc[1] = static_cast<int>(lt.x & 4095u);
+  }
+  __syncthreads();
+  const int t_y = smisc[0], t_x = smisc[1];
+  constexpr uint32_t tag = 1u;  // cleared by the forward kernel before this kernel can start
+  auto finish = [&]() {
+    // This kernel is the last of the call's chain and the next call's forward kernel waits only for it:
+    // completing after the fill kernel (our programmatic predecessor, which never blocks) makes "K2 done"
+    // imply "K3 done", so a late fill CTA can never see the next call's re-armed chunk counter.
+    ptx::pdl_wait();
+  };
+  int32_t* idx_b = p.index ? p.index + static_cast<size_t>(b) * p.T_y : nullptr;
+  if (t_y <= 0) {  // invalid lengths: the path stays all-zero
+    if (idx_b)
+      for (int y = tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
+    finish();
+    return;
+  }
+  const int g_top = (t_y - 1) >> 5;
+  const uint2* bits_b = p.bits + static_cast<size_t>(b) * p.G * p.TXP;
+  const int nfw = (t_x + p.cols_per_warp - 1) / p.cols_per_warp;  // forward warps that write this utterance's words
+  uint32_t* stage = sstage + static_cast<size_t>(warp) * p.TXS;
+  const int qp = (t_x + 31) / 32;
+
+  for (int g = warp; g <= g_top; g += nw) {
+    const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
+    if (g < g_top) {
+      // wait for the group's words: an element is valid once it carries this call's tag.  Poll ONE element per
+      // forward warp (the last column it owns, or the last valid column) with back-off -- 1000 warps re-reading
+      // whole rows would saturate the L2 -- then read the row and check every tag.
+      for (;;) {
+        bool ok = true;
+        if (lane < nfw) ok = __ldcg(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
+        if (__all_sync(0xffffffffu, ok)) {
+          for (int x = lane; x < t_x; x += 32) {
+            const uint2 el = __ldcg(row + x);
+            stage[x] = el.x;
+            ok = ok && el.y == tag;
+          }
+          if (__all_sync(0xffffffffu, ok)) break;
+        }
+        __nanosleep(200);
+      }
+      __syncwarp();
+      uint32_t* dec = p.dec16 ? nullptr : sdec + static_cast<size_t>(g) * p.TXS;
+      uint16_t* ex = sexit + static_cast<size_t>(g) * p.TXS;
+      if (qp <= 1) walk_group<1>(stage, dec, ex, t_x, lane);
+      else if (qp <= 2) walk_group<2>(stage, dec, ex, t_x, lane);
+      else if (qp <= 4) walk_group<4>(stage, dec, ex, t_x, lane);
+      else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane);
+      else walk_group<8>(stage, dec, ex, t_x, lane);
+      __syncwarp();
+    } else {
+      // top group, whose entry (t_y-1, t_x-1) is known.  The walk can visit at most 32 columns; lane l
+      // holds the decision word of column t_x-1-l, 32 ballots transpose them into one mask per frame, and
+      // the walk itself is then pure register arithmetic (no dependent shared-memory loads).
+      const int rt = (t_y - 1) & 31;
+      const int col = t_x - 1 - lane;
+      uint32_t w = 0u;
+      for (;;) {
+        bool ok = true;
+        if (col >= 0) {
+          const uint2 el = __ldcg(row + col);
+          w = el.x;
+          ok = el.y == tag;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(50);
+      }
+      uint32_t pos = 0, decw = 0;
+#pragma unroll
+      for (int r = 31; r >= 0; --r) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (w >> (31 - r)) & 1u);  // bit l: decision of column t_x-1-l
+        if (r <= rt) {
+          const uint32_t d = (m >> pos) & 1u;
+          decw |= d << r;
+          pos += d;
+        }
+      }
+      if (lane == 0) {
+        sentry[g_top] = t_x - 1;
+        if (!p.dec16) sdec[static_cast<size_t>(g_top) * p.TXS + t_x - 1] = decw;
+        smisc[2] = t_x - 1 - static_cast<int>(pos);  // entry of the group below
+        smisc[3] = static_cast<int>(decw);
+      }
+    }
+  }
+  __syncthreads();  // all tables are in shared memory
+  if (warp == 0) {
+    // chain over the groups below the top one: entry - popc(decisions)
+    int cur = smisc[2];
+    for (int g = g_top - 1; g >= 0; --g) {
+      if (lane == 0) sentry[g] = cur;
+      cur = p.dec16 ? static_cast<int>(sexit[static_cast<size_t>(g) * p.TXS + cur])
+                    : cur - __popc(sdec[static_cast<size_t>(g) * p.TXS + cur]);
+    }
+  } else if (warp == 1 && p.path) {
+    // the zero-fill must be complete before the ones are dropped
+    if (lane == 0) {
+      while (ptx::ld_acquire_gpu_u32(reinterpret_cast<const uint32_t*>(p.fill_counters + 1)) <
+             static_cast<uint32_t>(p.nchunks))
+        __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  // per-frame index: entry of the frame's group minus the steps taken above the frame
+  unsigned char* path_b = p.path ? p.path + static_cast<size_t>(b) * p.T_y * p.T_x * p.es : nullptr;
+  if (!p.dec16) {
+    for (int y = tid; y < p.T_y; y += blockDim.x) {
+      int v = -1;
+      if (y < t_y) {
+        const int g = y >> 5, r = y & 31;
+        const int en = sentry[g];
+        const uint32_t dec = sdec[static_cast<size_t>(g) * p.TXS + en];
+        v = en - __popc(static_cast<uint32_t>(static_cast<unsigned long long>(dec) >> (r + 1)));
+        if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + v) * p.es, p.es, p.one);
+      }
+      if (idx_b) idx_b[y] = v;
+    }
+  } else {
+    // 16-bit tables keep only the exits: one thread per group re-walks it from its real entry, reading the
+    // group's words from the scratch (L2-resident)
+    if (idx_b)
+      for (int y = t_y + tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
+    for (int g = tid; g <= g_top; g += blockDim.x) {
+      const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
+      int cur = sentry[g];
+      const uint32_t topw = static_cast<uint32_t>(smisc[3]);
+      for (int r = (g == g_top) ? ((t_y - 1) & 31) : 31; r >= 0; --r) {
+        const int y = (g << 5) + r;
+        if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + cur) * p.es, p.es, p.one);
+        if (idx_b) idx_b[y] = cur;
+        const uint32_t bit = (g == g_top) ? (topw >> r) & 1u : (__ldcg(row + cur).x >> (31 - r)) & 1u;
+        cur -= static_cast<int>(bit);
+      }
+    }
+  }
+  if (tid == 0) tl_max(p.tl, 4);
+  finish();
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
@@ -222,7 +445,7 @@ static unsigned long long* g_trace = nullptr;
 
 struct Layout {
   int G, TXP_max;
-  size_t off_status, off_lens, off_index, off_bits, total;
+  size_t off_status, off_lens, off_lenstag, off_index, off_bits, total;
 };
 
 // Scratch layout is independent of the tuning (bits rows are padded for the widest K).
@@ -236,9 +459,10 @@ static Layout scratch_layout(int B, int T_y, int T_x) {
   auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
   L.off_status = 0;
   L.off_lens = 256;
-  L.off_index = up(L.off_lens + static_cast<size_t>(B) * 2 * 4);
+  L.off_lenstag = up(L.off_lens + static_cast<size_t>(B) * 2 * 4);
+  L.off_index = up(L.off_lenstag + static_cast<size_t>(B) * 8);
   L.off_bits = up(L.off_index + static_cast<size_t>(B) * T_y * 4);
-  L.total = up(L.off_bits + static_cast<size_t>(B) * L.G * L.TXP_max * 4);
+  L.total = up(L.off_bits + static_cast<size_t>(B) * L.G * L.TXP_max * 8);  // streaming mode: {word, tag} pairs
   return L;
 }
 
@@ -269,7 +493,8 @@ static FwdSmem fwd_smem_layout(int W, int S, int BR, uint32_t slot_bytes, int G,
   return m;
 }
 
-static bool pick_fwd_config(int T_y, int T_x, FwdConfig* cfg) {
+// want_fused: -1 fused if it fits else unfused, 0 unfused, 1 fused or fail
+static bool pick_fwd_config(int T_y, int T_x, int want_fused, FwdConfig* cfg) {
   const uint32_t budget = 200 * 1024;
   int K = g_tune_K;
   // keep the block small: <= 7 warps besides the producer get the full register budget
@@ -286,7 +511,7 @@ static bool pick_fwd_config(int T_y, int T_x, FwdConfig* cfg) {
   const int G = (T_y + 31) / 32;
   const int TXP = W * 32 * K;
   // first choice: fused (bits + exit tables in shared memory, >= 3 ring stages); else unfused
-  for (int fused = (g_tune_fused == 0 ? 0 : 1); fused >= (g_tune_fused == 1 ? 1 : 0); --fused) {
+  for (int fused = (want_fused == 0 ? 0 : 1); fused >= (want_fused == 1 ? 1 : 0); --fused) {
     int H = 0;
     if (fused) {
       H = g_tune_H ? g_tune_H : 4;
@@ -378,12 +603,40 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     return MAS_E_ALIGN;
   const Layout L = scratch_layout(B, T_y, T_x);
   if (scratch_bytes < L.total) return MAS_E_SCRATCH;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  // Backtrack mode (mas_set_tuning2): 2 = streaming kernel on the idle SMs while the forward kernel runs
+  // (per-group tables of every group + one staging row per warp must fit in its shared memory), 1 = fused
+  // into the forward kernel (helper warps), 0 = separate kernel after the forward kernel.
+  const int TXS = T_x | 1;  // odd shared-memory row stride
+  const int G_ = (T_y + 31) / 32;
+  int bt_warps = G_ + 1 < 16 ? (G_ + 1 < 2 ? 2 : G_ + 1) : 16;
+  size_t bs_smem = (static_cast<size_t>(G_) * TXS + static_cast<size_t>(bt_warps) * TXS + G_ + 16) * 4;
+  int dec16 = 0;
+  if (bs_smem > 200 * 1024) {  // long utterances: 16-bit exit columns instead of 32-bit decision words
+    dec16 = 1;
+    bs_smem = (static_cast<size_t>(G_) * TXS / 2 + 1 + static_cast<size_t>(bt_warps) * TXS + G_ + 16) * 4;
+  }
+  const bool stream_ok = bs_smem <= 200 * 1024 && (g_debug_kernels & 7) == 7;
+  int mode = g_tune_fused;
+  if (mode == 2 && !stream_ok) return MAS_E_UNSUPPORTED;
   FwdConfig fc;
-  if (!pick_fwd_config(T_y, T_x, &fc)) return MAS_E_UNSUPPORTED;
+  if (!pick_fwd_config(T_y, T_x, mode == 2 ? 0 : mode, &fc)) return MAS_E_UNSUPPORTED;
+  // Automatic choice, from the measurements in DESIGN.md section 6: back-to-back calls run 2 % faster with the
+  // fused backtrack (45.3 vs 46.2 us at c2), so it is taken when its tables fit next to the ring; when they
+  // do not (long utterances), the streaming kernel hides the backtrack behind the forward kernel instead of
+  // running it afterwards (c4: 331 -> 2xx us).
+  if (mode < 0 && !fc.fused && stream_ok) mode = 2;
+  const bool stream = mode == 2;
 
   unsigned char* sc = static_cast<unsigned char*>(scratch);
   int32_t* status = reinterpret_cast<int32_t*>(sc + L.off_status);
   int32_t* lens = reinterpret_cast<int32_t*>(sc + L.off_lens);
+  uint2* lenstag = reinterpret_cast<uint2*>(sc + L.off_lenstag);
   int32_t* index = index_out ? index_out : reinterpret_cast<int32_t*>(sc + L.off_index);
   uint32_t* bits = reinterpret_cast<uint32_t*>(sc + L.off_bits);
 
@@ -392,6 +645,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
   fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
   fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
+  fp.lenstag = stream ? lenstag : nullptr;
   fp.wo_counters = status + 4;
   fp.pdl = g_tune_pdl;
   fp.trace = g_trace;
@@ -407,7 +661,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   }
 
   // K2: backtrack (only when the decision bits did not fit in shared memory)
-  if (!fc.fused && (g_debug_kernels & 2)) {
+  if (!fc.fused && !stream && (g_debug_kernels & 2)) {
     BtParams bp{};
     bp.bits = bits; bp.lens = lens; bp.index = index; bp.tl = g_timeline;
     bp.T_y = T_y; bp.TXP = fp.TXP; bp.G = L.G;
@@ -433,13 +687,8 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   }
 
   // K3: dense path
+  int nchunks = 0;
   if (path_out && (g_debug_kernels & 4)) {
-    if (g_num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (g_num_sms <= 0) g_num_sms = 148;
-    }
     WoParams wp{};
     wp.out = static_cast<unsigned char*>(path_out);
     wp.index = index;
@@ -448,9 +697,11 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     wp.rows = static_cast<long long>(B) * T_y;
     wp.bytes = wp.rows * T_x * es;
     wp.nchunks = static_cast<int>((wp.bytes + kWoChunk - 1) / kWoChunk);
+    nchunks = wp.nchunks;
     wp.T_x = T_x;
     wp.es = es;
     wp.one = one_bits(path_dtype);
+    wp.ones = stream ? 0 : 1;
     // few enough CTAs that all of them are resident at once on the SMs the forward kernel leaves idle
     // (they all have to run phase B; a CTA that starts only after the forward kernel adds tail latency)
     int grid = wp.nchunks < 2 * g_num_sms ? wp.nchunks : 2 * g_num_sms;
@@ -466,6 +717,36 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
       wo_attr = true;
     }
     e = launch_pdl(mas_writeout_kernel, dim3(grid), dim3(256), static_cast<size_t>(wo_smem), st, wp);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    count_launch();
+  }
+
+  // K2 (streaming variant): backtracks while K1 runs; launched last, so that everything it waits for (K1's
+  // words, K3's zero-fill) comes from EARLIER kernels of the stream -- tools that serialise kernels (ncu)
+  // then simply find everything ready.
+  if (stream) {
+    BsParams sp{};
+    sp.bits = reinterpret_cast<const uint2*>(bits); sp.lenstag = lenstag;
+    sp.index = index_out;  // only when the caller wants it
+    sp.path = (path_out && (g_debug_kernels & 4)) ? static_cast<unsigned char*>(path_out) : nullptr;
+    sp.fill_counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;
+    sp.nchunks = nchunks;
+    sp.T_y = T_y; sp.T_x = T_x; sp.TXP = fp.TXP; sp.G = L.G; sp.TXS = TXS;
+    sp.cols_per_warp = 32 * fc.K;
+    sp.dec16 = dec16;
+    sp.es = es; sp.one = one_bits(path_dtype);
+    sp.tl = g_timeline;
+    // not co-resident with a forward CTA either (same trick as the write-out kernel)
+    long long excl = 229LL * 1024 - static_cast<long long>(fc.sm.total);
+    if (excl < 0 || excl > 72 * 1024) excl = 0;
+    const size_t smem = bs_smem > static_cast<size_t>(excl) ? bs_smem : static_cast<size_t>(excl);
+    static bool bs_attr = false;
+    if (!bs_attr) {
+      e = cudaFuncSetAttribute(mas_backtrack_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      bs_attr = true;
+    }
+    e = launch_pdl(mas_backtrack_stream_kernel, dim3(B), dim3(32 * bt_warps), smem, st, sp);
     if (e != cudaSuccess) return static_cast<int>(e);
     count_launch();
   }
