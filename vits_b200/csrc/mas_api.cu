@@ -17,9 +17,9 @@ namespace {
 
 // State cached by the host entry (single caller thread, like the reference).
 struct HostCtx {
-  static constexpr int kChunks = 8;   // utterance groups pipelined over PCIe
-  static constexpr int kStreams = 3;
-  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+  static constexpr int kChunks = 16;  // utterance groups pipelined over PCIe
+  static constexpr int kStreams = 4;
+  cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr, nullptr};
   void* d_values = nullptr;
   void* d_paths = nullptr;
   void* d_lens = nullptr;
