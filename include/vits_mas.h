@@ -131,6 +131,15 @@ int mas_expand_prior(const int32_t* index, const float* m_p, const float* logs_p
                      int B, int C, int T_y, int T_x, mas_stream_t stream);
 int mas_generate_path(const float* duration, const float* mask, int64_t mask_sb, int64_t mask_sy, int64_t mask_sx,
                       float* path, int B, int T_y, int T_x, mas_stream_t stream);
+/*
+ * mas_kl_from_index -- kl_loss (losses.py:43-60) fused with the prior expansion that feeds it
+ *   (SynthesizerTrn.py:247-248): out2[0] = sum over (b,c,y) of (logs_p - logs_q - 0.5 + 0.5 (z_p - m_p)^2
+ *   exp(-2 logs_p)) * z_mask[b,y] with m_p, logs_p [B,C,T_x] gathered along `index` on the fly, out2[1] =
+ *   sum of z_mask; the loss is out2[0] / out2[1].  z_p, logs_q fp32 [B,C,T_y]; z_mask fp32 [B,T_y]; out2 two
+ *   doubles on the device (overwritten).
+ */
+int mas_kl_from_index(const int32_t* index, const float* z_p, const float* logs_q, const float* m_p, const float* logs_p,
+                      const float* z_mask, double* out2, int B, int C, int T_y, int T_x, mas_stream_t stream);
 
 /* Number of kernel launches the library has issued since load (bench.py's gpu_launches). */
 uint64_t mas_launch_count(void);

@@ -102,3 +102,48 @@ def test_durations_and_prior_expansion_gpu(oracle, shape):
     ((m_ref * g1).sum() + (l_ref * g2).sum()).backward()
     torch.testing.assert_close(gm, m_p.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(gl, logs_p.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_kl_loss_matches_reference(oracle):
+    """losses.py imports only torch: check the restatement against the reference's own function when it is here."""
+    import importlib.util
+    import sys
+    ref = "/root/reference/losses.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    spec = importlib.util.spec_from_file_location("ref_losses", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(5)
+    z_p, logs_q, m_p, logs_p = (torch.randn(2, 6, 17, generator=g) * s for s in (1.0, 0.3, 1.0, 0.3))
+    z_mask = (torch.arange(17)[None, :] < torch.tensor([17, 11])[:, None]).float()[:, None, :]
+    want = mod.kl_loss(z_p, logs_q, m_p, logs_p, z_mask)
+    assert torch.equal(oracle.kl_loss_torch(z_p, logs_q, m_p, logs_p, z_mask), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 200, 70, 192), (2, 1024, 192, 192), (2, 333, 257, 5)])
+def test_kl_loss_from_index_gpu(oracle, shape):
+    import vits_b200
+    B, T_y, T_x, C = shape
+    rng = np.random.default_rng(7 * B + T_x)
+    nc = torch.from_numpy((rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)).cuda()
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    ty, tx = torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()
+    index = vits_b200.maximum_path_index(nc, y_lengths=ty, x_lengths=tx)
+    attn = vits_b200.maximum_path_from_lengths(nc, ty, tx).unsqueeze(1)
+    z_mask = (torch.arange(T_y, device="cuda")[None, :] < ty[:, None]).float()[:, None, :]
+    leaves = [torch.randn(B, C, T_y, device="cuda").requires_grad_(), (torch.randn(B, C, T_y, device="cuda") * 0.3).requires_grad_(),
+              torch.randn(B, C, T_x, device="cuda").requires_grad_(), (torch.randn(B, C, T_x, device="cuda") * 0.3).requires_grad_()]
+    z_p, logs_q, m_p, logs_p = leaves
+    got = vits_b200.kl_loss_from_index(index, z_p, logs_q, m_p, logs_p, z_mask)
+    # the reference: expand with the einsums on the dense path, then losses.kl_loss
+    want = oracle.kl_loss_torch(z_p, logs_q, oracle.expand_prior_torch(attn, m_p), oracle.expand_prior_torch(attn, logs_p), z_mask)
+    torch.testing.assert_close(got, want.detach(), rtol=2e-5, atol=1e-6)     # summation order differs (fp64 accumulation here)
+    got.backward()
+    grads = [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    want.backward()
+    for a, t in zip(grads, leaves):
+        torch.testing.assert_close(a, t.grad, rtol=1e-4, atol=1e-7)

@@ -16,6 +16,6 @@ from . import monotonic_align  # noqa: F401
 from .monotonic_align import maximum_path, maximum_path_from_lengths, maximum_path_index  # noqa: F401
 from .neg_cent import neg_cent  # noqa: F401
 from . import shard  # noqa: F401
-from .alignment_ops import expand_prior, generate_path, path_durations  # noqa: F401
+from .alignment_ops import expand_prior, generate_path, kl_loss_from_index, path_durations  # noqa: F401
 
 __version__ = "0.1.0"

@@ -82,6 +82,54 @@ def expand_prior(index: torch.Tensor, m_p: torch.Tensor, logs_p: Optional[torch.
     return _Expand.apply(index, m_p, logs_p)
 
 
+class _KlIndex(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, index, z_p, logs_q, m_p, logs_p, z_mask):
+        idx = _check_index(index)
+        B, T_y = idx.shape
+        z, lq, m, lp = (t.detach().float().contiguous() for t in (z_p, logs_q, m_p, logs_p))
+        mk = z_mask.detach().float().reshape(B, T_y).contiguous()
+        C, T_x = m.shape[1], m.shape[2]
+        out = torch.empty(2, dtype=torch.float64, device=idx.device)
+        with torch.cuda.device(idx.device):
+            rc = _lib.lib().mas_kl_from_index(idx.data_ptr(), z.data_ptr(), lq.data_ptr(), m.data_ptr(), lp.data_ptr(),
+                                              mk.data_ptr(), out.data_ptr(), B, C, T_y, T_x, _stream(idx.device))
+        _lib.check(rc, "mas_kl_from_index")
+        ctx.save_for_backward(idx, z, lq, m, lp, mk, out)
+        return (out[0] / out[1]).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, z, lq, m, lp, mk, out = ctx.saved_tensors
+        scale = (g.double() / out[1]).float()
+        # recompute on the expanded statistics (our gather), then scatter the text-side gradients back
+        m_e, lp_e = _Expand.apply(idx, m, lp)
+        w = mk[:, None, :] * scale
+        iv = torch.exp(-2.0 * lp_e)
+        d = z - m_e
+        g_z = d * iv * w
+        g_lq = -w.expand_as(z)
+        g_me = -g_z
+        g_lpe = (1.0 - d * d * iv) * w
+        valid = idx >= 0
+        at = idx.clamp_min(0).to(torch.int64)[:, None, :].expand_as(z)
+
+        def scatter(t):
+            t = t * valid[:, None, :]
+            return torch.zeros_like(m).scatter_add_(2, at, t)
+
+        return None, g_z, g_lq.contiguous(), scatter(g_me), scatter(g_lpe), None
+
+
+def kl_loss_from_index(index: torch.Tensor, z_p: torch.Tensor, logs_q: torch.Tensor, m_p: torch.Tensor,
+                       logs_p: torch.Tensor, z_mask: torch.Tensor) -> torch.Tensor:
+    """The reference's ``kl_loss(z_p, logs_q, m_p, logs_p, z_mask)`` (losses.py:43-60) with the TEXT-side prior
+    statistics ``m_p, logs_p [B, C, T_x]`` and the alignment ``index`` instead of the expanded ``[B, C, T_y]``
+    tensors: the expansion (SynthesizerTrn.py:247-248) happens inside the reduction.  ``z_mask`` is ``[B, 1, T_y]``.
+    Differentiable with respect to z_p, logs_q, m_p, logs_p."""
+    return _KlIndex.apply(index, z_p, logs_q, m_p, logs_p, z_mask)
+
+
 def generate_path(duration: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """Drop-in for the reference's ``commons.generate_path(duration, mask)``: duration ``[b, 1, t_x]``,
     mask ``[b, 1, t_y, t_x]``; returns the ``[b, 1, t_y, t_x]`` path in ``mask``'s dtype."""

@@ -184,6 +184,11 @@ int mas_generate_path(const float* duration, const float* mask, int64_t mask_sb,
   return mas::generate_path(duration, mask, mask_sb, mask_sy, mask_sx, path, B, T_y, T_x, static_cast<cudaStream_t>(stream));
 }
 
+int mas_kl_from_index(const int32_t* index, const float* z_p, const float* logs_q, const float* m_p, const float* logs_p,
+                      const float* z_mask, double* out2, int B, int C, int T_y, int T_x, mas_stream_t stream) {
+  return mas::kl_from_index(index, z_p, logs_q, m_p, logs_p, z_mask, out2, B, C, T_y, T_x, static_cast<cudaStream_t>(stream));
+}
+
 uint64_t mas_launch_count(void) { return mas::g_launches.load(std::memory_order_relaxed); }
 
 /* Tuning hooks for benchmarks (not part of the reference-facing surface). 0 = automatic. */

@@ -130,3 +130,83 @@ int generate_path(const float* duration, const float* mask, int64_t msb, int64_t
 }
 
 }  // namespace mas
+
+// ---- kl_loss on the compact index (losses.py:43-60 fused with the prior expansion) -------------------
+// sum over (b,c,y) of (logs_p - logs_q - 0.5 + 0.5 (z_p - m_p)^2 exp(-2 logs_p)) * z_mask[b,y], with
+// m_p/logs_p gathered along the alignment on the fly (m_p[b,c,index[b,y]]) instead of read from expanded
+// [B,C,T_y] tensors; also sum of z_mask.  Accumulates in double: out[0] += kl sum, out[1] += mask sum
+// (out[1] is added once, by the c0 == 0 CTAs).
+namespace mas {
+
+__global__ void __launch_bounds__(256) mas_kl_index_kernel(const int32_t* __restrict__ index, const float* __restrict__ z_p,
+                                                           const float* __restrict__ logs_q, const float* __restrict__ m_p,
+                                                           const float* __restrict__ logs_p, const float* __restrict__ z_mask,
+                                                           double* __restrict__ out, int C, int T_y, int T_x) {
+  extern __shared__ float rows[];  // [2][kCPB][T_x]
+  __shared__ double red[2][8];
+  const int b = blockIdx.x;
+  const int c0 = blockIdx.y * kCPB;
+  const int nc = min(kCPB, C - c0);
+  for (int i = threadIdx.x; i < nc * T_x; i += blockDim.x) {
+    rows[i] = m_p[(static_cast<size_t>(b) * C + c0) * T_x + i];
+    rows[kCPB * T_x + i] = logs_p[(static_cast<size_t>(b) * C + c0) * T_x + i];
+  }
+  __syncthreads();
+  double acc = 0.0, macc = 0.0;
+  for (int y = threadIdx.x; y < T_y; y += blockDim.x) {
+    const int x = index[static_cast<size_t>(b) * T_y + y];
+    const float mk = z_mask[static_cast<size_t>(b) * T_y + y];
+    const bool ok = x >= 0 && x < T_x;
+    macc += mk;
+    float part = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kCPB; ++c) {
+      if (c < nc) {
+        const size_t o = (static_cast<size_t>(b) * C + c0 + c) * T_y + y;
+        const float m = ok ? rows[c * T_x + x] : 0.0f;        // the einsum yields 0 on frames without a 1
+        const float lp = ok ? rows[(kCPB + c) * T_x + x] : 0.0f;
+        const float d = z_p[o] - m;
+        part += (lp - logs_q[o] - 0.5f) + 0.5f * (d * d) * __expf(-2.0f * lp);
+      }
+    }
+    acc += static_cast<double>(part * mk);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    macc += __shfl_xor_sync(0xffffffffu, macc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = acc;
+    red[1][threadIdx.x >> 5] = macc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, m = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) {
+      a += red[0][w];
+      m += red[1][w];
+    }
+    atomicAdd(out, a);
+    if (c0 == 0) atomicAdd(out + 1, m);
+  }
+}
+
+int kl_from_index(const int32_t* index, const float* z_p, const float* logs_q, const float* m_p, const float* logs_p,
+                  const float* z_mask, double* out, int B, int C, int T_y, int T_x, cudaStream_t st) {
+  if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || B > 65535) return MAS_E_BAD_SHAPE;
+  if (!index || !z_p || !logs_q || !m_p || !logs_p || !z_mask || !out) return MAS_E_NULL;
+  const size_t smem = static_cast<size_t>(2) * kCPB * T_x * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mas_kl_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  mas_kl_index_kernel<<<dim3(B, (C + kCPB - 1) / kCPB), 256, smem, st>>>(index, z_p, logs_q, m_p, logs_p, z_mask, out, C, T_y, T_x);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace mas

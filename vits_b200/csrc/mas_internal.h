@@ -26,6 +26,9 @@ int expand_prior(const int32_t* index, const float* m_p, const float* logs_p, fl
 int generate_path(const float* duration, const float* mask, int64_t msb, int64_t msy, int64_t msx, float* path, int B,
                   int T_y, int T_x, cudaStream_t st);
 
+int kl_from_index(const int32_t* index, const float* z_p, const float* logs_q, const float* m_p, const float* logs_p,
+                  const float* z_mask, double* out, int B, int C, int T_y, int T_x, cudaStream_t st);
+
 // mas_neg_cent.cu
 int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
              int B, int C, int T_y, int T_x, cudaStream_t st);
