@@ -153,9 +153,13 @@ void mas_set_neg_cent_impl(int impl);
 /* Benchmark isolation: bit0 forward DP, bit1 backtrack, bit2 write-out; default 7 (all). */
 void mas_set_debug_kernels(int mask);
 /* fused: -1 automatic, 0 separate backtrack kernel after the forward kernel, 1 backtrack fused into the
- * forward kernel, 2 streaming backtrack kernel on the idle SMs while the forward kernel runs;
- * helpers: helper warps of the fused kernel (0 = automatic). */
+ * forward kernel, 2 streaming backtrack kernel on the idle SMs while the forward kernel runs, 3 the same
+ * behind the wavefront forward kernel; helpers: helper warps of the fused kernel (0 = automatic). */
 void mas_set_tuning2(int fused, int helpers);
+/* Wavefront forward kernel: wavefront 0 = never choose it automatically, -1 = automatic; ring_mode 1..3 =
+ * linear ring (mirror slot) with that many frames of skew between lanes, 4 = select ring (skew 1);
+ * ring_slots = chunks of 32 frames per warp (>= skew + 2, or 3); cols_per_lane in {1,2,4}; 0 = automatic. */
+void mas_set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane);
 /* Debug timeline: device pointer to 8 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
  * kernels update with min start / max end %globaltimer stamps; NULL disables. */
 void mas_set_timeline(void* dev_ptr);

@@ -83,13 +83,39 @@ def test_every_kernel_configuration(mp, oracle, K, R):
         t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
         want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
         for stages, pdl, fused, helpers in ((2, 1, 0, 0), (5, 0, 0, 0), (3, 1, 1, 1), (4, 0, 1, 4), (0, 1, -1, 0),
-                                            (3, 1, 2, 0), (0, 0, 2, 0)):
+                                            (3, 1, 2, 0), (0, 0, 2, 0), (0, 1, 3, 0)):
             L.mas_set_tuning(K, R, stages, pdl)
             L.mas_set_tuning2(fused, helpers)
             got = _gpu_path(mp, nc, t_ys, t_xs)
             np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} fused={fused} {shape}")
     L.mas_set_tuning(0, 0, 0, 1)
     L.mas_set_tuning2(-1, 0)
+
+
+@pytest.mark.parametrize("ring_mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("K", [1, 2, 4])
+def test_wavefront_forward_kernel_configurations(mp, oracle, K, ring_mode):
+    """The wavefront forward kernel (mode 3): every columns-per-lane instantiation, the linear ring at skew 1..3
+    and the select ring, minimal and deep rings, TMA and cp.async chunk loads (T_x % 4 != 0), with/without PDL."""
+    L = mp._lib.lib()
+    rng = np.random.default_rng(50 * K + ring_mode)
+    smin = {1: 3, 2: 4, 3: 5, 4: 3}[ring_mode]
+    try:
+        for shape in [(3, 150, 96), (2, 333, 100), (2, 260, 129), (2, 300, 31), (2, 700, 190)]:
+            B, T_y, T_x = shape
+            nc = (rng.standard_normal(shape) * 2 - 1).astype(np.float32)
+            t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+            want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+            for slots, pdl in ((smin, 1), (0, 0), (0, 1)):
+                L.mas_set_tuning(0, 0, 0, pdl)
+                L.mas_set_tuning2(3, 0)
+                L.mas_set_tuning3(-1, ring_mode, slots, K)
+                got = _gpu_path(mp, nc, t_ys, t_xs)
+                np.testing.assert_array_equal(got, want, err_msg=f"K={K} ring={ring_mode} S={slots} pdl={pdl} {shape}")
+    finally:
+        L.mas_set_tuning(0, 0, 0, 1)
+        L.mas_set_tuning2(-1, 0)
+        L.mas_set_tuning3(-1, 0, 0, 0)
 
 
 def test_streaming_backtrack_with_16_bit_tables(mp, oracle):

@@ -198,6 +198,9 @@ void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl) 
 void mas_set_neg_cent_impl(int impl) { mas::set_neg_cent_impl(impl); }
 void mas_set_debug_kernels(int mask) { mas::set_debug_kernels(mask); }
 void mas_set_tuning2(int fused, int helpers) { mas::set_tuning2(fused, helpers); }
+void mas_set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane) {
+  mas::set_tuning3(wavefront, ring_mode, ring_slots, cols_per_lane);
+}
 void mas_set_timeline(void* dev_ptr) { mas::set_timeline(static_cast<unsigned long long*>(dev_ptr)); }
 void mas_set_trace(void* dev_ptr) { mas::set_trace(static_cast<unsigned long long*>(dev_ptr)); }
 

@@ -11,55 +11,9 @@
 #include "../../include/vits_mas.h"
 #include "mas_internal.h"
 #include "ptx_sm100.cuh"
+#include "mas_common.cuh"
 
 namespace mas {
-
-constexpr float kNeg = -1e9f;  // core.pyx:7 max_neg_val
-
-// ------------------------------------------------------------------------------------------------
-// lengths from the mask, as monotonic_align/__init__.py:17-18: t_y = sum_y mask[b,y,0],
-// t_x = sum_x mask[b,0,x]; float sums are truncated like numpy's astype(int32).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mask_at(const void* p, int dtype, int64_t off) {
-  switch (dtype) {
-    case MAS_F32: return static_cast<const float*>(p)[off];
-    case MAS_F16: return __half2float(static_cast<const __half*>(p)[off]);
-    case MAS_BF16: return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[off]);
-    case MAS_F64: return static_cast<const double*>(p)[off];
-    case MAS_U8: return static_cast<const uint8_t*>(p)[off];
-    case MAS_I8: return static_cast<const int8_t*>(p)[off];
-    case MAS_I16: return static_cast<const int16_t*>(p)[off];
-    case MAS_I32: return static_cast<const int32_t*>(p)[off];
-    default: return static_cast<double>(static_cast<const int64_t*>(p)[off]);
-  }
-}
-
-// strided sum of n mask elements starting at `base` (element stride `stride`), dtype resolved once so
-// the loads of one thread are independent and overlap
-template <typename T>
-__device__ __forceinline__ double mask_sum_t(const T* base, int64_t stride, int n, int tid, int nthr) {
-  double s = 0.0;
-#pragma unroll 4
-  for (int i = tid; i < n; i += nthr) s += static_cast<double>(static_cast<float>(base[i * stride]));
-  return s;
-}
-__device__ __forceinline__ double mask_sum(const void* p, int dtype, int64_t off, int64_t stride, int n, int tid, int nthr) {
-  switch (dtype) {
-    case MAS_F32: return mask_sum_t(static_cast<const float*>(p) + off, stride, n, tid, nthr);
-    case MAS_U8: return mask_sum_t(static_cast<const uint8_t*>(p) + off, stride, n, tid, nthr);
-    default: {
-      double s = 0.0;
-      for (int i = tid; i < n; i += nthr) s += mask_at(p, dtype, off + i * stride);
-      return s;
-    }
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // ------------------------------------------------------------------------------------------------
 // K1: forward DP
@@ -96,20 +50,6 @@ struct FwdParams {
   uint32_t slot_bytes;
   FwdSmem sm;
 };
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// timeline slots: 0 fwd first start, 1 fwd last DP done, 2 fwd last end, 3 bt first start, 4 bt last end,
-//                 5 wo first start, 6 wo last zero-fill done, 7 wo last end
-__device__ __forceinline__ void tl_min(unsigned long long* tl, int slot) {
-  if (tl) atomicMin(tl + slot, globaltimer_ns());
-}
-__device__ __forceinline__ void tl_max(unsigned long long* tl, int slot) {
-  if (tl) atomicMax(tl + slot, globaltimer_ns());
-}
 
 // One frame of the recurrence for the K columns of a lane.
 //   DIAG: this frame may hold the diagonal cell x == y in column `jd` of the lane for which `diag`
@@ -192,13 +132,6 @@ __device__ __forceinline__ void load_row(float (&c)[K], const float* __restrict_
 #pragma unroll
     for (int j = 0; j < K; ++j) c[j] = row[min(xl + j, T_x - 1)];
   }
-}
-
-// One backtrack step (core.pyx:32-33) given the decision word of the current column.  The
-// forward kernel already folded `index == y` (bit forced to 1) and `index != 0` (column 0
-// forced to 0) into the stored bits.
-__device__ __forceinline__ int bt_step(int cur, int r, uint32_t word) {
-  return cur - static_cast<int>((word >> (31 - r)) & 1u);
 }
 
 // BIG: more than 7 warps besides the producer (block of up to 1024 threads, 64 registers each);
@@ -291,8 +224,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   } else {
     double sy = 0.0, sx = 0.0;
     const int64_t base = static_cast<int64_t>(b) * p.msb;
-    sy = mask_sum(p.mask, p.mask_dtype, base, p.msy, p.T_y, tid, blockDim.x);
-    sx = mask_sum(p.mask, p.mask_dtype, base, p.msx, p.T_x, tid, blockDim.x);
+    mask_sums(p.mask, p.mask_dtype, base, p.msy, p.T_y, p.msx, p.T_x, tid, blockDim.x, sy, sx);
     sy = warp_sum(sy);
     sx = warp_sum(sx);
     if (lane == 0) {

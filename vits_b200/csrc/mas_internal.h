@@ -16,6 +16,7 @@ size_t maximum_path_scratch_bytes(int B, int T_y, int T_x);
 void set_tuning(int K, int R, int S, int pdl);
 void set_debug_kernels(int mask);
 void set_tuning2(int fused, int helpers);
+void set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane);
 void set_timeline(unsigned long long* dev_ptr);
 void set_trace(unsigned long long* dev_ptr);
 

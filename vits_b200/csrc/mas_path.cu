@@ -29,9 +29,13 @@
 // and at x==0 exactly as core.pyx:17-27; ties stay (strict <); index==y forces a step.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
+#include <cuda.h>
+
 #include "mas_forward.cuh"
+#include "mas_dp.cuh"
 
 namespace mas {
 
@@ -439,6 +443,8 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
 // host side
 // ------------------------------------------------------------------------------------------------
 static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
+static int g_tune_wf = -1, g_tune_ring = 0, g_tune_wfS = 0, g_tune_wfK = 0;  // wavefront forward kernel (mas_set_tuning3)
+static int g_fill_div = 4;  // streaming mode: fill CTAs = g_fill_div/4 x SM count (tunable through MAS_FILL_DIV)
 static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only)
 static unsigned long long* g_timeline = nullptr;
 static unsigned long long* g_trace = nullptr;
@@ -550,6 +556,101 @@ static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int 
   }
 }
 
+struct DpConfig {
+  int K, W, S, BR, linear, skew;
+  DpSmem sm;
+};
+
+constexpr uint32_t kSmemMax = 227 * 1024;  // per CTA on sm_100
+constexpr uint32_t kSmemSM = 228 * 1024;   // per SM
+
+static DpSmem dp_smem_layout(int K, int W, int nphys, int S, int BR) {
+  auto up = [](uint32_t v) { return (v + 127u) & ~127u; };
+  DpSmem m{};
+  m.ring = 0;
+  m.bnd = up(static_cast<uint32_t>(W) * nphys * kRows * 32u * K * 4u);
+  m.bars = up(m.bnd + static_cast<uint32_t>(W + 1) * BR * 4u);
+  m.prog = up(m.bars + static_cast<uint32_t>(W) * S * 8u);
+  m.red = up(m.prog + static_cast<uint32_t>(W) * 4u);
+  m.total = up(m.red + 64u * 8u + 16u);
+  return m;
+}
+
+// A superstep of a warp reads frames 32s-31*D .. 32s+31 (D = skew between lanes): Q+1 = ceil(31D/32)+1 chunks
+// are live and at least one more must be in flight, so the linear ring needs S >= Q+2 slots plus the mirror;
+// the select ring (D = 1, no mirror) needs 3.  D = 3 hides the SHFL latency completely, D = 1 not at all.
+static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg) {
+  int K = g_tune_wfK;
+  if (K == 0) K = 2;  // K = 2 keeps the per-step dependency chain short and fills one scheduler per 64 columns
+  if (K != 1 && K != 2 && K != 4) return false;
+  int W = (T_x + 32 * K - 1) / (32 * K);
+  while (W > 8 && K < 4) {
+    K *= 2;
+    W = (T_x + 32 * K - 1) / (32 * K);
+  }
+  if (W > 8) return false;
+  const int BR = 256;
+  const uint32_t budget = 208 * 1024;
+  const uint32_t slotset = static_cast<uint32_t>(W) * kRows * 32u * K * 4u;  // one chunk of every warp
+  const int nphys = static_cast<int>((budget - 12 * 1024) / slotset);
+  int linear = 1, skew = 0;
+  if (g_tune_ring >= 1 && g_tune_ring <= 3) skew = g_tune_ring;
+  else if (g_tune_ring == 4) { linear = 0; skew = 1; }
+  else if (nphys >= 4) skew = 1;       // measured at c2: 25.3 us with skew 1 or 2, 29.8 us with skew 3 (more lag per hop)
+  else { linear = 0; skew = 1; }
+  const int Q = (31 * skew + 31) / 32;
+  const int smin = linear ? Q + 2 : 3;
+  int S = linear ? nphys - 1 : nphys;
+  if (S > 8) S = 8;
+  if (g_tune_wfS) S = g_tune_wfS;
+  if (S < smin) return false;
+  const DpSmem m = dp_smem_layout(K, W, linear ? S + 1 : S, S, BR);
+  if (m.total > kSmemMax) return false;
+  (void)T_y;
+  *cfg = DpConfig{K, W, S, BR, linear, skew, m};
+  return true;
+}
+
+static cudaError_t launch_dp_dispatch(int K, const CUtensorMap& tmap, const DpParams& p, int skew, bool linear, cudaStream_t st) {
+  switch (K) {
+    case 1: return launch_dp_k1(tmap, p, skew, linear, st);
+    case 2: return launch_dp_k2(tmap, p, skew, linear, st);
+    case 4: return launch_dp_k4(tmap, p, skew, linear, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [B*T_y][T_x] fp32 tensor, box = [R frames][32*K columns]; out-of-range cells read as zero
+static bool make_tensor_map(CUtensorMap* tm, const float* nc, long long rows, int T_x, int R, int cols) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(T_x), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(T_x) * 4u};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(cols), static_cast<cuuint32_t>(R)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(nc), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename Kern, typename Params>
 static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Params& p) {
   cudaLaunchConfig_t cfg{};
@@ -604,6 +705,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   const Layout L = scratch_layout(B, T_y, T_x);
   if (scratch_bytes < L.total) return MAS_E_SCRATCH;
   if (g_num_sms == 0) {
+    if (const char* fd = getenv("MAS_FILL_DIV")) g_fill_div = atoi(fd) > 0 ? atoi(fd) : g_fill_div;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -623,15 +725,23 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   }
   const bool stream_ok = bs_smem <= 200 * 1024 && (g_debug_kernels & 7) == 7;
   int mode = g_tune_fused;
-  if (mode == 2 && !stream_ok) return MAS_E_UNSUPPORTED;
-  FwdConfig fc;
-  if (!pick_fwd_config(T_y, T_x, mode == 2 ? 0 : mode, &fc)) return MAS_E_UNSUPPORTED;
-  // Automatic choice, from the measurements in DESIGN.md section 6: back-to-back calls run 2 % faster with the
-  // fused backtrack (45.3 vs 46.2 us at c2), so it is taken when its tables fit next to the ring; when they
-  // do not (long utterances), the streaming kernel hides the backtrack behind the forward kernel instead of
-  // running it afterwards (c4: 331 -> 2xx us).
+  if ((mode == 2 || mode == 3) && !stream_ok) return MAS_E_UNSUPPORTED;
+  // mode 3: streaming backtrack behind the WAVEFRONT forward kernel (mas_dp.cuh)
+  DpConfig dc{};
+  const bool wf_ok = stream_ok && T_x <= 512 && pick_dp_config(T_y, T_x, &dc);
+  if (mode == 3 && !wf_ok) return MAS_E_UNSUPPORTED;
+  if (mode < 0 && wf_ok && g_tune_wf != 0) mode = 3;
+  FwdConfig fc{};
+  if (mode != 3 && !pick_fwd_config(T_y, T_x, mode == 2 ? 0 : mode, &fc)) return MAS_E_UNSUPPORTED;
+  // Automatic choice, from the measurements in DESIGN.md section 6: the wavefront kernel with the streaming
+  // backtrack when it fits (T_x <= 512); else the fused backtrack when its tables fit next to the ring; else
+  // the stage-granular forward kernel with the streaming backtrack (long utterances).
   if (mode < 0 && !fc.fused && stream_ok) mode = 2;
-  const bool stream = mode == 2;
+  const bool stream = mode == 2 || mode == 3;
+  const bool wavefront = mode == 3;
+  const int TXP = wavefront ? dc.W * 32 * dc.K : fc.W * 32 * fc.K;
+  const int cols_per_warp = 32 * (wavefront ? dc.K : fc.K);
+  const long long fwd_smem = wavefront ? dc.sm.total : fc.sm.total;
 
   unsigned char* sc = static_cast<unsigned char*>(scratch);
   int32_t* status = reinterpret_cast<int32_t*>(sc + L.off_status);
@@ -641,20 +751,37 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   uint32_t* bits = reinterpret_cast<uint32_t*>(sc + L.off_bits);
 
   // K1: forward (+ backtrack when fused)
-  FwdParams fp{};
-  fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
-  fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
-  fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
-  fp.lenstag = stream ? lenstag : nullptr;
-  fp.wo_counters = status + 4;
-  fp.pdl = g_tune_pdl;
-  fp.trace = g_trace;
-  fp.B = B; fp.T_y = T_y; fp.T_x = T_x;
-  fp.S = fc.S; fp.W = fc.W; fp.H = fc.H; fp.TXP = fc.W * 32 * fc.K; fp.G = L.G; fp.BR = fc.BR;
-  fp.fused = fc.fused; fp.slot_bytes = fc.slot_bytes; fp.sm = fc.sm;
-  const bool vec = (reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0 && T_x >= fc.K;
   cudaError_t e = cudaSuccess;
-  if (g_debug_kernels & 1) {
+  if (wavefront) {
+    DpParams dp{};
+    dp.nc = neg_cent; dp.t_ys = t_ys; dp.t_xs = t_xs;
+    dp.mask = mask; dp.mask_dtype = mask_dtype; dp.msb = msb; dp.msy = msy; dp.msx = msx;
+    dp.lens = lens; dp.status = status; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
+    dp.wo_counters = status + 4;
+    dp.pdl = g_tune_pdl;
+    dp.B = B; dp.T_y = T_y; dp.T_x = T_x;
+    dp.S = dc.S; dp.W = dc.W; dp.TXP = TXP; dp.G = L.G; dp.BR = dc.BR;
+    dp.sm = dc.sm;
+    CUtensorMap tmap{};
+    dp.use_tma = ((reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0) ? 1 : 0;
+    if (dp.use_tma && !make_tensor_map(&tmap, neg_cent, static_cast<long long>(B) * T_y, T_x, kRows, 32 * dc.K))
+      dp.use_tma = 0;
+    e = launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    count_launch();
+  } else if (g_debug_kernels & 1) {
+    FwdParams fp{};
+    fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
+    fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
+    fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
+    fp.lenstag = stream ? lenstag : nullptr;
+    fp.wo_counters = status + 4;
+    fp.pdl = g_tune_pdl;
+    fp.trace = g_trace;
+    fp.B = B; fp.T_y = T_y; fp.T_x = T_x;
+    fp.S = fc.S; fp.W = fc.W; fp.H = fc.H; fp.TXP = TXP; fp.G = L.G; fp.BR = fc.BR;
+    fp.fused = fc.fused; fp.slot_bytes = fc.slot_bytes; fp.sm = fc.sm;
+    const bool vec = (reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0 && T_x >= fc.K;
     e = launch_fwd_dispatch(fc.K, vec, fp, fc.R, st);
     if (e != cudaSuccess) return static_cast<int>(e);
     count_launch();
@@ -664,7 +791,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   if (!fc.fused && !stream && (g_debug_kernels & 2)) {
     BtParams bp{};
     bp.bits = bits; bp.lens = lens; bp.index = index; bp.tl = g_timeline;
-    bp.T_y = T_y; bp.TXP = fp.TXP; bp.G = L.G;
+    bp.T_y = T_y; bp.TXP = TXP; bp.G = L.G;
     bp.TXS = T_x | 1;  // odd stride: neighbouring groups hit different banks in phase 3
     const size_t per_group = static_cast<size_t>(bp.TXS) * 6 + 32 * 4 + 4;
     int GS = static_cast<int>((160 * 1024) / per_group);
@@ -704,11 +831,13 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     wp.ones = stream ? 0 : 1;
     // few enough CTAs that all of them are resident at once on the SMs the forward kernel leaves idle
     // (they all have to run phase B; a CTA that starts only after the forward kernel adds tail latency)
-    int grid = wp.nchunks < 2 * g_num_sms ? wp.nchunks : 2 * g_num_sms;
+    // (streaming mode has the whole DP time for the fill: fewer CTAs = less HBM contention for the forward kernel)
+    const int fill_ctas = (stream ? g_fill_div : 2) * g_num_sms / (stream ? 4 : 1);
+    int grid = wp.nchunks < fill_ctas ? wp.nchunks : fill_ctas;
     if (grid < 1) grid = 1;
     // Dynamic shared memory the write-out does not use: just enough that its CTAs cannot be co-resident
     // with a forward CTA; they still pack several per SM on the SMs the forward kernel leaves idle.
-    long long wo_smem = 229LL * 1024 - static_cast<long long>(fc.sm.total);
+    long long wo_smem = 229LL * 1024 - fwd_smem;
     if (wo_smem < 0 || wo_smem > 56 * 1024) wo_smem = 0;  // forward CTA too small to exclude cheaply
     static bool wo_attr = false;
     if (!wo_attr) {
@@ -731,13 +860,13 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     sp.path = (path_out && (g_debug_kernels & 4)) ? static_cast<unsigned char*>(path_out) : nullptr;
     sp.fill_counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;
     sp.nchunks = nchunks;
-    sp.T_y = T_y; sp.T_x = T_x; sp.TXP = fp.TXP; sp.G = L.G; sp.TXS = TXS;
-    sp.cols_per_warp = 32 * fc.K;
+    sp.T_y = T_y; sp.T_x = T_x; sp.TXP = TXP; sp.G = L.G; sp.TXS = TXS;
+    sp.cols_per_warp = cols_per_warp;
     sp.dec16 = dec16;
     sp.es = es; sp.one = one_bits(path_dtype);
     sp.tl = g_timeline;
     // not co-resident with a forward CTA either (same trick as the write-out kernel)
-    long long excl = 229LL * 1024 - static_cast<long long>(fc.sm.total);
+    long long excl = 229LL * 1024 - fwd_smem;
     if (excl < 0 || excl > 72 * 1024) excl = 0;
     const size_t smem = bs_smem > static_cast<size_t>(excl) ? bs_smem : static_cast<size_t>(excl);
     static bool bs_attr = false;
@@ -767,6 +896,12 @@ void set_tuning(int K, int R, int S, int pdl) {
   g_tune_R = R;
   g_tune_S = S;
   g_tune_pdl = pdl;
+}
+void set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane) {
+  g_tune_wf = wavefront;
+  g_tune_ring = ring_mode;
+  g_tune_wfS = ring_slots;
+  g_tune_wfK = cols_per_lane;
 }
 void set_tuning2(int fused, int helpers) {
   g_tune_fused = fused;

@@ -58,10 +58,62 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
-// ---- GPU-scope acquire load (polling a counter another kernel increments with fence + atomic) ----
+// ---- 2-D tiled TMA load (tensor map) global -> shared, completion on an mbarrier -------------
+// c0 = innermost coordinate (elements), c1 = row.  dst 128-byte aligned.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- Ampere-style 4-byte async copy with zero fill (src_bytes 0 or 4), completion on an mbarrier ----
+__device__ __forceinline__ void cp_async4_zfill(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- small flags: shared (CTA scope) and global (GPU scope) ----------------------------------
+// Flags in shared memory between warps of one CTA.  Plain volatile accesses: the LSU keeps one thread's
+// shared-memory accesses in order, and the PTX acquire/release forms cost a MEMBAR + L1 invalidate each.
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_f32(float* p, float v) {
+  asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile_s32(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- volatile shared-memory vector loads by 32-bit shared address (+ byte offset immediate) ----
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 
