@@ -400,8 +400,9 @@ def run_ours(args, rank, world, local_rank):
                        "parity_checked": parity, "multi_gpu_verified": verified},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "path_breakdown": breakdown,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (100.7e6 if not primary_ragged else None), "traffic_note": "full-length c2, ncu --set full: mas_forward 50.4 MB DRAM read + mas_writeout 50.3 MB written (profiles/); not captured for the variable-length variant", "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
-                         "kernel": "maximum_path chain (mas_forward with fused backtrack + mas_writeout, PDL-overlapped, "
+                         "traffic": (105.4e6 if not primary_ragged else None), "traffic_note": "full-length c2, ncu --set full (profiles/): mas_dp 50.4 MB DRAM read + 1.6 MB of tagged decision words written (and 3.1 MB of tag clears), mas_writeout 50.3 MB written; not captured for the variable-length variant", "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                         "kernel": "maximum_path chain (mas_dp wavefront forward kernel + mas_writeout zero-fill + "
+                                   "mas_backtrack_stream, concurrent on disjoint SMs through programmatic dependent launch, "
                                    "timed as one unit with CUDA events on the launching stream)",
                          "phase_timeline_us": kernels_ms},
         }
@@ -468,8 +469,8 @@ def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=5):
     (mas_set_timeline): microseconds relative to the first forward CTA's start, median of `reps`."""
     import torch
     import vits_b200
-    names = ["fwd_first_start", "fwd_last_dp_done", "fwd_last_end(backtrack tail done)", "bt_first_start", "bt_last_end",
-             "wo_first_start", "wo_last_zero_fill_done", "wo_last_end"]
+    names = ["fwd_first_start", "fwd_last_dp_done", "fwd_last_end", "bt_first_start", "bt_last_end",
+             "wo_first_start", "wo_last_zero_fill_done", "wo_last_end|wavefront:lengths_known"]
     tl = torch.zeros(8, dtype=torch.int64, device=dev)
     out = {}
     try:
