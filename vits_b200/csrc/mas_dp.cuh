@@ -100,7 +100,15 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
   constexpr uint32_t SLOTB = R * ROWB;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  const int dw = tid >> 5;
+  // Warp roles.  Up to three DP warps sit on schedulers 0..2 and every helper warp (two producers, the lengths
+  // warp) on scheduler 3 (warp ids 3, 7, 11; the warps in between exit at once): a helper that shares a
+  // scheduler with a DP warp steals its issue slots while it polls (measured: 3-4 us on the DP).  With more DP
+  // warps the helpers simply follow them.
+  const int wid = tid >> 5;
+  const bool spread = p.W <= 3;
+  const int NP = p.W <= 3 ? 2 : 4;                                   // producer warps
+  const int dw = spread ? (wid < 3 ? (wid < p.W ? wid : -1) : (wid & 3) == 3 ? p.W + (wid >> 2) : -1)
+                        : wid;                                       // 0..W-1 DP, W..W+NP-1 producers, W+NP lengths
   const int lane = tid & 31;
   const int S = p.S, W = p.W, BR = p.BR;
   const int nphys = LINEAR ? S + 1 : S;
@@ -200,8 +208,8 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
   // Nothing in the recurrence needs them: every DP warp runs (columns >= t_x compute garbage nobody reads) and
   // t_y only says when to stop.  With a cold mask the column walk is DRAM-row-activation bound (64 utterances x
   // 1024 strided elements: ~8 us measured), which this takes off the critical path.
-  const int NW_ALL = static_cast<int>(blockDim.x >> 5);
-  if (dw == NW_ALL - 1) {
+  if (dw < 0) return;  // filler warps
+  if (dw == W + NP) {
     // Counters and tags were cleared before the barrier above: make that visible GPU-wide, then let the
     // dependent kernels start.  Only this warp pays for the fence; the DP warps are already running.
     if (lane == 0) {
@@ -255,7 +263,6 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
     // warp has finished superstep c-S+Q (all its lanes are past chunk c-S): they watch the progress counters.
     // Producer q of NP serves the rings w with w % NP == q; lane w tracks ring w. ----
     const int q = dw - W;
-    const int NP = NW_ALL - 1 - W;
     int ci = nspec;        // lane w: next chunk of warp w's ring ...
     int cs = nspec % S;    // ... and its slot
     const bool mine = lane < W && (lane % NP) == q;
@@ -542,7 +549,7 @@ inline cudaError_t launch_dp_t(const CUtensorMap& tmap, const DpParams& p, cudaS
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.B);
-  cfg.blockDim = dim3(32 * (p.W + (p.W <= 3 ? 2 : 4) + 1));  // DP warps + producer warps + the lengths warp
+  cfg.blockDim = dim3(p.W <= 3 ? 32 * 12 : 32 * (p.W + 4 + 1));  // see the warp roles in the kernel
   cfg.dynamicSmemBytes = p.sm.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
