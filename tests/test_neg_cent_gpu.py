@@ -89,3 +89,21 @@ def test_end_to_end_path_agreement(oracle, shape):
     # and on the *same* neg_cent the paths are bit-identical
     same = vits_b200.maximum_path_from_lengths(nc_ref, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
     np.testing.assert_array_equal(same.cpu().numpy().astype(np.int32), want)
+
+
+def test_maximum_path_from_stats(oracle):
+    """Both stages in one call, lengths instead of a mask: equals maximum_path(neg_cent(...), attn_mask)."""
+    import vits_b200
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, C, T_y, T_x = 3, 192, 260, 90
+    z = torch.randn(B, C, T_y, generator=g, device="cuda")
+    m = torch.randn(B, C, T_x, generator=g, device="cuda")
+    ls = torch.randn(B, C, T_x, generator=g, device="cuda") * 0.3
+    y_len = torch.tensor([260, 200, 131], device="cuda")
+    x_len = torch.tensor([90, 71, 45], device="cuda")
+    mask = oracle.attn_mask(x_len, y_len, T_x, T_y, torch.float32)
+    want = vits_b200.maximum_path(vits_b200.neg_cent(z, m, ls), mask)
+    got = vits_b200.maximum_path_from_stats(z, m, ls, x_len, y_len)
+    assert torch.equal(got, want)
+    idx = vits_b200.maximum_path_from_stats(z, m, ls, x_len, y_len, index=True)
+    assert idx.dtype == torch.int32 and torch.equal(torch.nn.functional.one_hot(idx.clamp_min(0).long(), T_x).float() * (idx >= 0)[..., None], want)

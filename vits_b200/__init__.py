@@ -7,6 +7,7 @@ Public surface:
     vits_b200.monotonic_align.maximum_path_from_lengths(...)   -- same, lengths instead of mask
     vits_b200.monotonic_align.maximum_path_index(...)          -- compact per-frame index
     vits_b200.neg_cent(z_p, m_p, logs_p)                       -- the contraction feeding it
+    vits_b200.maximum_path_from_stats(z_p, m_p, logs_p, x_len, y_len)  -- both, without a mask tensor
     vits_b200.path_durations / expand_prior / generate_path    -- the path's consumers on the compact index, and
                                                                   commons.generate_path
     vits_b200.shard                                            -- batch sharding across GPUs (no data-path collective)
@@ -14,7 +15,7 @@ Public surface:
 from . import _lib  # noqa: F401
 from . import monotonic_align  # noqa: F401
 from .monotonic_align import maximum_path, maximum_path_from_lengths, maximum_path_index  # noqa: F401
-from .neg_cent import neg_cent  # noqa: F401
+from .neg_cent import maximum_path_from_stats, neg_cent  # noqa: F401
 from . import shard  # noqa: F401
 from .alignment_ops import expand_prior, generate_path, kl_loss_from_index, path_durations  # noqa: F401
 

@@ -44,3 +44,16 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torc
                             scratch.numel(), B, C, T_y, T_x, stream)
         _lib.check(rc, "mas_neg_cent")
     return out
+
+
+def maximum_path_from_stats(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor, x_lengths: torch.Tensor,
+                            y_lengths: torch.Tensor, *, index: bool = False) -> torch.Tensor:
+    """``z_p, m_p, logs_p -> path`` in one call: the contraction (SynthesizerTrn.py:223-232) followed by the
+    alignment search (:235), with the lengths given directly -- no ``[B, T_y, T_x]`` mask is built or read
+    (SynthesizerTrn.py:234).  ``index=True`` returns the compact int32 ``[B, T_y]`` form instead of the dense
+    path.  (The two stages still exchange ``neg_cent`` through HBM; SURVEY.md 8f rank 1 would fuse them.)"""
+    from .monotonic_align import maximum_path_from_lengths, maximum_path_index
+    nc = neg_cent(z_p, m_p, logs_p)
+    if index:
+        return maximum_path_index(nc, y_lengths=y_lengths, x_lengths=x_lengths)
+    return maximum_path_from_lengths(nc, y_lengths, x_lengths)
