@@ -143,6 +143,21 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
 
     med, best, n = time_core(core, budget_s * 0.25)
     res["core_only"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med}
+    # (3) what training pays with the reference today: the wrapper fed CUDA tensors (blocking D2H of neg_cent and
+    # of the mask sums, serial CPU loop, H2D of the path)
+    try:
+        if torch.cuda.is_available():
+            nc_d, mask_d = nc.cuda(), mask.cuda()
+
+            def wrapped_cuda():
+                out = mas_oracle.maximum_path(nc_d, mask_d, core=core)
+                torch.cuda.synchronize()
+                return out
+            med, best, n = timeit(wrapped_cuda, budget_s * 0.15)
+            res["wrapper_cuda_tensors"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med}
+            del nc_d, mask_d
+    except Exception as ex:  # pragma: no cover
+        res["wrapper_cuda_tensors"] = {"error": str(ex)}
     threads = len(os.sched_getaffinity(0))
     if omp is not None:
         os.environ.setdefault("OMP_NUM_THREADS", str(threads))
