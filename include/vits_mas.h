@@ -45,7 +45,8 @@ enum {
 enum {
   MAS_STATUS_TX_GT_TY = 1,   /* some utterance had t_x > t_y                     */
   MAS_STATUS_EMPTY = 2,      /* some utterance had t_x < 1 or t_y < 1            */
-  MAS_STATUS_TOO_LONG = 4    /* some utterance had t_y > T_y or t_x > T_x        */
+  MAS_STATUS_TOO_LONG = 4,   /* some utterance had t_y > T_y or t_x > T_x        */
+  MAS_STATUS_TIMEOUT = 8     /* internal: a kernel gave up waiting for another   */
 };
 
 int mas_abi_version(void);

@@ -231,6 +231,7 @@ struct BsParams {
   int T_y, T_x, TXP, G;
   int TXS;                  // shared-memory row stride in words (odd)
   int cols_per_warp;        // 32*K of the forward kernel: ceil(t_x / cols_per_warp) warps arrive per group
+  int32_t* status;          // sticky MAS_STATUS_* bits (MAS_STATUS_TIMEOUT: a poll below gave up)
   int dec16;                // 1: tables hold 16-bit exit columns (long utterances), the per-frame index is re-walked from the words
   int es;
   unsigned long long one;
@@ -294,9 +295,23 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
 
   ptx::pdl_launch_dependents();  // the next call's forward kernel may set up while we run
   if (tid == 0) tl_min(p.tl, 3);
+  // Watchdog: everything this kernel polls is produced by EARLIER kernels of the stream, so a poll can only
+  // fail to terminate if one of them died; give up after 2 s (status bit, garbage result) rather than hang.
+  const unsigned long long t_start = globaltimer_ns();
+  auto expired = [&]() {
+    if (globaltimer_ns() - t_start < 2000000000ull) return false;
+    atomicOr(p.status, MAS_STATUS_TIMEOUT);
+    return true;
+  };
   if (tid == 0) {
     uint2 lt;
-    while ((lt = __ldcg(p.lenstag + b)).y != 1u) __nanosleep(100);
+    while ((lt = __ldcg(p.lenstag + b)).y != 1u) {
+      if (expired()) {
+        lt = make_uint2(0u, 1u);
+        break;
+      }
+      __nanosleep(100);
+    }
     smisc[0] = static_cast<int>(lt.x >> 12);
     smisc[1] = static_cast<int>(lt.x & 4095u);
   }
@@ -339,6 +354,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
           }
           if (__all_sync(0xffffffffu, ok)) break;
         }
+        if (__any_sync(0xffffffffu, expired())) break;
         __nanosleep(200);
       }
       __syncwarp();
@@ -365,6 +381,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
           ok = el.y == tag;
         }
         if (__all_sync(0xffffffffu, ok)) break;
+        if (__any_sync(0xffffffffu, expired())) break;
         __nanosleep(50);
       }
       uint32_t pos = 0, decw = 0;
@@ -398,8 +415,10 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     // the zero-fill must be complete before the ones are dropped
     if (lane == 0) {
       while (ptx::ld_acquire_gpu_u32(reinterpret_cast<const uint32_t*>(p.fill_counters + 1)) <
-             static_cast<uint32_t>(p.nchunks))
+             static_cast<uint32_t>(p.nchunks)) {
+        if (expired()) break;
         __nanosleep(100);
+      }
     }
   }
   __syncthreads();
@@ -855,7 +874,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   // then simply find everything ready.
   if (stream) {
     BsParams sp{};
-    sp.bits = reinterpret_cast<const uint2*>(bits); sp.lenstag = lenstag;
+    sp.bits = reinterpret_cast<const uint2*>(bits); sp.lenstag = lenstag; sp.status = status;
     sp.index = index_out;  // only when the caller wants it
     sp.path = (path_out && (g_debug_kernels & 4)) ? static_cast<unsigned char*>(path_out) : nullptr;
     sp.fill_counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;

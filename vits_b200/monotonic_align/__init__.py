@@ -58,6 +58,8 @@ def _decode_status(bits: int) -> str:
         msgs.append("an utterance has t_x < 1 or t_y < 1")
     if bits & _lib.MAS_STATUS_TOO_LONG:
         msgs.append("an utterance is longer than the padded tensor")
+    if bits & 8:
+        msgs.append("internal: a kernel gave up waiting for another (results are invalid)")
     return "; ".join(msgs)
 
 
