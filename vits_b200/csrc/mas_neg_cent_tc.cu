@@ -52,7 +52,7 @@ constexpr int PCB = 32;           // channels per prep-kernel CTA
 constexpr int A_ARR = M * CB * 2; // bytes of one A operand array per stage (8 KB)
 constexpr int A_LBO = M * 16;     // bytes between 8-channel chunks of A
 constexpr int W_LOAD = 0, W_MMA = 1, W_EPI0 = 2, N_EPI = 8, W_ZL0 = 10, W_CV0 = 14, N_ZL = 4, N_CV = 8, N_WARPS = 22;
-constexpr int ZS_MAX = 4;             // fp32 z staging ring between the z loaders and the converters (p.ZS slots)
+constexpr int ZS_MAX = 6;             // fp32 z staging ring between the z loaders and the converters (p.ZS slots)
 constexpr int Z_STAGE = CB * M * 4;   // 8 KB
 constexpr int TMEM_COLS = 512;    // two accumulator buffers of up to 256 columns
 }  // namespace tc
@@ -70,7 +70,7 @@ struct TcParams {
   int NCB;               // channel blocks = pipeline stages per tile (ceil(C/CB))
   int tiles;             // B*MT*NTL
   int ZS;                // z staging slots (3, or fewer when the column tile is wide)
-  int dbg;               // timing bisection only (wrong results): 1 no stores, 2 no A conversion, 4 no B copy, 8 no MMA; 16 trace
+  int dbg;               // timing bisection only (wrong results): 1 no stores, 2 no A conversion, 4 no B copy, 8 no MMA; 16 trace; 32 no z loads; 64 no wait for prep; 128 prep only; 256 GEMM only
   unsigned long long* trace;  // dbg & 16: CTA 0 appends (tag, clock) pairs
 };
 
@@ -102,6 +102,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
@@ -177,70 +182,65 @@ struct PrepParams {
   int B, C, T_x, Nt, NTL, NCB;
 };
 
-// One CTA per (utterance, column tile, 32-channel block).  Thread = (8-channel chunk q, 4 consecutive
-// columns): 16 vector loads in flight, then four 16-byte groups per operand array.  The per-column
-// bias partial of the CTA's 32 channels goes to bias[pb]; the GEMM epilogue sums the partials.
-__global__ void __launch_bounds__(256) neg_cent_prep_kernel(const PrepParams p) {
-  __shared__ float sred[4][256];
-  const int nt = blockIdx.x, b = blockIdx.y, pb = blockIdx.z;
+// One small CTA (64 threads) per (utterance, 16 columns of a column tile, 32-channel block); thread =
+// (8-channel chunk q, ONE text column): 16 scalar loads up front, 8 elements of work, one 16-byte group per
+// operand array.  The earlier shape -- 4 columns per thread in CTAs of Nt threads -- left ~16 warps per SM,
+// each running 1500 dependent instructions behind its loads, and took 12 us, all of it in front of the GEMM.
+// Two-warp CTAs fill the SMs to 64 warps and have no wave tail (Nt is a multiple of 16).
+// The per-column bias partial of the CTA's 32 channels goes to bias[pb]; the GEMM epilogue sums the partials.
+__global__ void __launch_bounds__(64) neg_cent_prep_kernel(const PrepParams p) {
+  __shared__ float sred[4][16];
+  const int ncg = p.Nt >> 4;
+  const int nt = blockIdx.x / ncg, cg = blockIdx.x - nt * ncg, b = blockIdx.y, pb = blockIdx.z;
   const int tid = threadIdx.x;
   ptx::pdl_launch_dependents();  // the GEMM kernel's A producers do not depend on us
-  const float* mb = p.m_p + static_cast<size_t>(b) * p.C * p.T_x;
-  const float* lb = p.logs_p + static_cast<size_t>(b) * p.C * p.T_x;
-  const int n0 = nt * p.Nt;
-  const int nquad = p.Nt >> 2;         // Nt is a multiple of 16
-  const int q = tid / nquad;           // chunk of 8 channels inside the block (blockDim = 4 * nquad)
-  const int n = (tid - q * nquad) * 4; // first of this thread's 4 columns
-  const int s0 = n0 + n;
+  const int q = tid >> 4;              // chunk of 8 channels inside the block
+  const int n = cg * 16 + (tid & 15);  // column inside the tile
+  const int s0 = nt * p.Nt + n;  // text column
+  const bool col_ok = s0 < p.T_x;
   const int d0 = pb * tc::PCB + q * 8;
   const int sb = d0 / tc::CB, chunk = (d0 % tc::CB) / 8;  // pipeline stage block and 8-channel chunk inside it
   const size_t arr = static_cast<size_t>(p.Nt) * (tc::CB / 8) * 16;  // bytes of one operand array of a stage block
-  unsigned char* dst0 = p.bops + ((static_cast<size_t>(b) * p.NTL + nt) * p.NCB + sb) * (4 * arr);
+  const float* mb = p.m_p + static_cast<size_t>(b) * p.C * p.T_x + (col_ok ? s0 : 0);
+  const float* lb = p.logs_p + static_cast<size_t>(b) * p.C * p.T_x + (col_ok ? s0 : 0);
   const float kHalfLog2Pi = 0.91893853320467274178f;
-  const bool vec = ((p.T_x & 3) == 0) && (s0 + 3 < p.T_x) &&
-                   ((reinterpret_cast<uintptr_t>(mb) | reinterpret_cast<uintptr_t>(lb)) & 15u) == 0;
-  float l[8][4], m[8][4];
+  float l[8], m[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int d = d0 + i;
-    if (d < p.C && vec) {
-      const float4 lv = *reinterpret_cast<const float4*>(lb + static_cast<size_t>(d) * p.T_x + s0);
-      const float4 mv = *reinterpret_cast<const float4*>(mb + static_cast<size_t>(d) * p.T_x + s0);
-      l[i][0] = lv.x; l[i][1] = lv.y; l[i][2] = lv.z; l[i][3] = lv.w;
-      m[i][0] = mv.x; m[i][1] = mv.y; m[i][2] = mv.z; m[i][3] = mv.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = d < p.C && s0 + j < p.T_x;
-        l[i][j] = ok ? lb[static_cast<size_t>(d) * p.T_x + s0 + j] : 0.0f;
-        m[i][j] = ok ? mb[static_cast<size_t>(d) * p.T_x + s0 + j] : 0.0f;
-      }
-    }
+  for (int i = 0; i < 8; ++i) {  // unconditional loads from a clamped address, masked below
+    const size_t off = static_cast<size_t>(min(d0 + i, p.C - 1)) * p.T_x;
+    l[i] = __ldg(lb + off);
+    m[i] = __ldg(mb + off);
   }
-  float bias[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  uint32_t ivh[4], ivl[4], mvh[4], mvl[4];
+  float bias = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t ivh[8], ivl[8], mvh[8], mvl[8];
+  for (int i2 = 0; i2 < 4; ++i2) {
+    uint32_t h[2][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool ok = d0 + i < p.C && s0 + j < p.T_x;
-      const float iv = ok ? __expf(-2.0f * l[i][j]) : 0.0f;  // :223 (ex2.approx: ~2 ulp, far inside the 1e-5 bar)
-      const float mv = m[i][j] * iv;                          // :229
-      if (ok) bias[j] += (-kHalfLog2Pi - l[i][j]) + (-0.5f * (m[i][j] * m[i][j])) * iv;  // :225, :231
-      split_bits(iv, ivh[i], ivl[i]);
-      split_bits(mv, mvh[i], mvl[i]);
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * i2 + e;
+      const bool ok = col_ok && d0 + i < p.C;
+      const float iv = ok ? __expf(-2.0f * l[i]) : 0.0f;  // :223 (ex2.approx: ~2 ulp, far inside the 1e-5 bar)
+      const float mv = m[i] * iv;                          // :229
+      if (ok) bias += (-kHalfLog2Pi - l[i]) + (-0.5f * (m[i] * m[i])) * iv;  // :225, :231
+      split_bits(iv, h[e][0], h[e][1]);
+      split_bits(mv, h[e][2], h[e][3]);
     }
-    unsigned char* dst = dst0 + (static_cast<size_t>(chunk) * p.Nt + n + j) * 16;
-    *reinterpret_cast<uint4*>(dst + 0 * arr) = make_uint4(pack2(ivh[0], ivh[1]), pack2(ivh[2], ivh[3]), pack2(ivh[4], ivh[5]), pack2(ivh[6], ivh[7]));
-    *reinterpret_cast<uint4*>(dst + 1 * arr) = make_uint4(pack2(ivl[0], ivl[1]), pack2(ivl[2], ivl[3]), pack2(ivl[4], ivl[5]), pack2(ivl[6], ivl[7]));
-    *reinterpret_cast<uint4*>(dst + 2 * arr) = make_uint4(pack2(mvh[0], mvh[1]), pack2(mvh[2], mvh[3]), pack2(mvh[4], mvh[5]), pack2(mvh[6], mvh[7]));
-    *reinterpret_cast<uint4*>(dst + 3 * arr) = make_uint4(pack2(mvl[0], mvl[1]), pack2(mvl[2], mvl[3]), pack2(mvl[4], mvl[5]), pack2(mvl[6], mvl[7]));
+    ivh[i2] = pack2(h[0][0], h[1][0]);
+    ivl[i2] = pack2(h[0][1], h[1][1]);
+    mvh[i2] = pack2(h[0][2], h[1][2]);
+    mvl[i2] = pack2(h[0][3], h[1][3]);
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) sred[q][n + j] = bias[j];
+  unsigned char* dst = p.bops + ((static_cast<size_t>(b) * p.NTL + nt) * p.NCB + sb) * (4 * arr) +
+                       (static_cast<size_t>(chunk) * p.Nt + n) * 16;
+  *reinterpret_cast<uint4*>(dst + 0 * arr) = make_uint4(ivh[0], ivh[1], ivh[2], ivh[3]);
+  *reinterpret_cast<uint4*>(dst + 1 * arr) = make_uint4(ivl[0], ivl[1], ivl[2], ivl[3]);
+  *reinterpret_cast<uint4*>(dst + 2 * arr) = make_uint4(mvh[0], mvh[1], mvh[2], mvh[3]);
+  *reinterpret_cast<uint4*>(dst + 3 * arr) = make_uint4(mvl[0], mvl[1], mvl[2], mvl[3]);
+  sred[q][tid & 15] = bias;
   __syncthreads();
-  if (tid < p.Nt)
-    p.bias[((static_cast<size_t>(pb) * p.B + b) * p.NTL + nt) * p.Nt + tid] =
+  if (tid < 16)
+    p.bias[((static_cast<size_t>(pb) * p.B + b) * p.NTL + nt) * p.Nt + n] =
         (sred[0][tid] + sred[1][tid]) + (sred[2][tid] + sred[3][tid]);
 }
 
@@ -260,12 +260,12 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
   // smem: [stage][A a2_hi | a2_lo | z_hi | z_lo | B iv_hi | iv_lo | mv_hi | mv_lo] ... barriers
   float* zstage = reinterpret_cast<float*>(smem + tc::STAGES * stage_bytes);  // [ZS][CB][M] fp32
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tc::STAGES * stage_bytes + p.ZS * tc::Z_STAGE);
-  uint64_t* full = bars;                         // [STAGES] count N_CV (A converters) + 1 (B loader) + B bytes
+  uint64_t* full = bars;                         // [STAGES] count N_CV/2 (one converter group) + 1 (B loader) + B bytes
   uint64_t* empty = full + tc::STAGES;           // [STAGES] count 1 (tcgen05.commit)
   uint64_t* t_full = empty + tc::STAGES;         // [2] count 1 (tcgen05.commit)
   uint64_t* t_empty = t_full + 2;                // [2] count 4 (epilogue warps)
   uint64_t* z_full = t_empty + 2;                // [ZS_MAX] count N_ZL
-  uint64_t* z_empty = z_full + tc::ZS_MAX;       // [ZS_MAX] count N_CV
+  uint64_t* z_empty = z_full + tc::ZS_MAX;       // [ZS_MAX] count N_CV/2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + tc::ZS_MAX);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256]
   unsigned long long* tsm = reinterpret_cast<unsigned long long*>(sbias + 512);  // debug trace log (dbg & 16 only)
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
 
   if (tid == 0) {
     for (int s = 0; s < tc::STAGES; ++s) {
-      ptx::mbar_init(&full[s], tc::N_CV + 1);
+      ptx::mbar_init(&full[s], tc::N_CV / 2 + 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     }
     for (int i = 0; i < tc::ZS_MAX; ++i) {
       ptx::mbar_init(&z_full[i], tc::N_ZL * 32);  // one asynchronous arrival per loader thread
-      ptx::mbar_init(&z_empty[i], tc::N_CV);
+      ptx::mbar_init(&z_empty[i], tc::N_CV / 2);
     }
     ptx::mbar_fence_init();
   }
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
   if (warp == tc::W_LOAD) {
     // ---------------- B loader ----------------
     if (lane == 0) {
-      ptx::pdl_wait();  // the prep kernel's tiles must be complete
+      if (!(p.dbg & 64)) ptx::pdl_wait();  // the prep kernel's tiles must be complete
       uint32_t it = 0;
       for (int lt = 0; lt < ntile_local; ++lt) {
         const int tile = blockIdx.x + lt * gridDim.x;
@@ -322,11 +322,14 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     }
   } else if (warp == tc::W_MMA) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // The whole warp runs this loop and one elected lane issues: with warp-uniform control flow the
+    // descriptors, the stage offset and the barrier addresses live in uniform registers.  (Inside an
+    // `if (lane == 0)` the same code kept them in vector registers and paid a chain of R2UR moves in front of
+    // every tcgen05.mma -- ~100 cycles of issue per 96-cycle MMA, with the tensor pipe waiting for this thread.)
+    {
       const uint32_t idesc = instr_desc(tc::M, Nt);
       // Base descriptors of the 4 A and 4 B operand arrays in stage 0; a stage only shifts the 14-bit
-      // address field (smem < 256 KB, so the add never carries out of it).  Building descriptors inside
-      // the loop cost ~300 cycles per stage of single-thread integer work with the tensor pipe idle.
+      // address field (smem < 256 KB, so the add never carries out of it).
       uint64_t adesc[4], bdesc[4];
       {
         const uint32_t a0 = ptx::smem_u32(smem);
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
         }
       }
       const uint32_t stage_step = stage_bytes >> 4;  // descriptor address units
+      const bool mma = !(p.dbg & 8);
       uint32_t it = 0;
       int s = 0;
       uint32_t par = 0;
@@ -347,31 +351,32 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
         for (int cb = 0; cb < p.NCB; ++cb, ++it) {
-          trace_ev(p, tsm, tcnt, 1, 0, it);
-          // test_wait first: ~10x cheaper than try_wait when the phase already completed (the usual case:
-          // the producers run ahead), and the tensor pipe only queues about one MMA, so every cycle this
-          // thread spends between two issues is an idle tensor core
+          if (lane == 0) trace_ev(p, tsm, tcnt, 1, 0, it);
+          // test_wait first: ~10x cheaper than try_wait when the phase already completed (the usual case)
           if (!ptx::mbar_test(&full[s], par)) ptx::mbar_wait(&full[s], par);
-          trace_ev(p, tsm, tcnt, 1, 2, it);
+          if (lane == 0) trace_ev(p, tsm, tcnt, 1, 2, it);
           tc_fence_after();
           const uint64_t soff = static_cast<uint64_t>(static_cast<uint32_t>(s) * stage_step);
-          if (!(p.dbg & 8)) {
-            // operand pairs: (a2_hi,iv_hi) (a2_hi,iv_lo) (a2_lo,iv_hi) (z_hi,mv_hi) (z_hi,mv_lo) (z_lo,mv_hi)
-            umma_bf16(d_tmem, adesc[0] + soff, bdesc[0] + soff, idesc, cb != 0 ? 1u : 0u);
-            umma_bf16(d_tmem, adesc[0] + soff, bdesc[1] + soff, idesc, 1u);
-            umma_bf16(d_tmem, adesc[1] + soff, bdesc[0] + soff, idesc, 1u);
-            umma_bf16(d_tmem, adesc[2] + soff, bdesc[2] + soff, idesc, 1u);
-            umma_bf16(d_tmem, adesc[2] + soff, bdesc[3] + soff, idesc, 1u);
-            umma_bf16(d_tmem, adesc[3] + soff, bdesc[2] + soff, idesc, 1u);
+          if (elect_one()) {
+            if (mma) {
+              // operand pairs: (a2_hi,iv_hi) (a2_hi,iv_lo) (a2_lo,iv_hi) (z_hi,mv_hi) (z_hi,mv_lo) (z_lo,mv_hi)
+              umma_bf16(d_tmem, adesc[0] + soff, bdesc[0] + soff, idesc, cb != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, adesc[0] + soff, bdesc[1] + soff, idesc, 1u);
+              umma_bf16(d_tmem, adesc[1] + soff, bdesc[0] + soff, idesc, 1u);
+              umma_bf16(d_tmem, adesc[2] + soff, bdesc[2] + soff, idesc, 1u);
+              umma_bf16(d_tmem, adesc[2] + soff, bdesc[3] + soff, idesc, 1u);
+              umma_bf16(d_tmem, adesc[3] + soff, bdesc[2] + soff, idesc, 1u);
+            }
+            umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+            if (cb == p.NCB - 1) umma_commit(&t_full[buf]);  // accumulator complete
           }
-          umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
-          trace_ev(p, tsm, tcnt, 1, 3, it);
+          __syncwarp();
+          if (lane == 0) trace_ev(p, tsm, tcnt, 1, 3, it);
           if (++s == tc::STAGES) {
             s = 0;
             par ^= 1u;
           }
         }
-        umma_commit(&t_full[buf]);  // accumulator complete
       }
     }
   } else if (warp >= tc::W_EPI0 && warp < tc::W_ZL0) {
@@ -381,7 +386,21 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     const int eh = (warp - tc::W_EPI0) >> 2;  // two warps share a lane quarter: even / odd column groups
     const int cq = 2 * (lane & 3);  // this lane's column pair inside each group of 8
-    ptx::pdl_wait();  // bias comes from the prep kernel
+    if (!(p.dbg & 64)) ptx::pdl_wait();  // bias comes from the prep kernel
+    constexpr int kBiasRegs = 8;
+    float bpart[kBiasRegs];
+    auto bias_fetch = [&](int lt_) {
+      const int tile_ = blockIdx.x + lt_ * gridDim.x;
+      const int nt_ = tile_ % p.NTL;
+      const int b_ = tile_ / (p.NTL * p.MT);
+      const int e = (warp - tc::W_EPI0) * 32 + lane;
+#pragma unroll
+      for (int sp = 0; sp < kBiasRegs; ++sp)
+        bpart[sp] = (e < Nt && sp < p.nsplit) ? p.bias[((static_cast<size_t>(sp) * p.B + b_) * p.NTL + nt_) * Nt + e] : 0.0f;
+      for (int sp = kBiasRegs; sp < p.nsplit; ++sp)  // more than 8 channel blocks (C > 256): summed right away
+        if (e < Nt) bpart[0] += p.bias[((static_cast<size_t>(sp) * p.B + b_) * p.NTL + nt_) * Nt + e];
+    };
+    bias_fetch(0);
     for (int lt = 0; lt < ntile_local; ++lt) {
       const int tile = blockIdx.x + lt * gridDim.x;
       const int nt = tile % p.NTL;
@@ -389,18 +408,19 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       const int b = tile / (p.NTL * p.MT);
       const int buf = lt & 1;
       const int n0 = nt * Nt;
-      // bias of this tile's columns -> shared memory (sum of the prep kernel's per-channel-block partials),
-      // fetched before we wait for the accumulator so its latency hides behind the MMAs
+      // bias of this tile's columns (sum of the prep kernel's per-channel-block partials): the partials were
+      // loaded into registers during the previous tile's drain and are only summed here, so their latency
+      // is never waited for (Nt <= 256 = one column per epilogue thread)
       {
-        float* sb = sbias + buf * 256;
         const int e = (warp - tc::W_EPI0) * 32 + lane;
-        for (int c = e; c < Nt; c += tc::N_EPI * 32) {
+        if (e < Nt) {
           float v = 0.0f;
-          for (int sp = 0; sp < p.nsplit; ++sp)
-            v += p.bias[((static_cast<size_t>(sp) * p.B + b) * p.NTL + nt) * Nt + c];
-          sb[c] = v;
+#pragma unroll
+          for (int sp = 0; sp < kBiasRegs; ++sp) v += bpart[sp];
+          sbias[buf * 256 + e] = v;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(tc::N_EPI * 32) : "memory");  // the epilogue warps only
+        if (lt + 1 < ntile_local) bias_fetch(lt + 1);
       }
       if (warp == tc::W_EPI0 && lane == 0) trace_ev(p, tsm, tcnt, 2, 0, lt);
       ptx::mbar_wait(&t_full[buf], (lt >> 1) & 1);
@@ -488,7 +508,8 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       if (use >= 1) ptx::mbar_wait(&z_empty[zs], (use - 1) & 1);  // converters finished reading the slot
       float* dst = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + fm;
       const int d0 = ld_cb * tc::CB;
-      if (vec16) {
+      if (p.dbg & 32) {
+      } else if (vec16) {
 #pragma unroll
         for (int k = 0; k < tc::CB / 4; ++k) {
           const int ch = ch0 + 4 * k;
@@ -523,46 +544,54 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     asm volatile("cp.async.wait_all;" ::: "memory");  // nothing may still be writing our shared memory at exit
   } else if (warp >= tc::W_CV0) {
     // ---------------- converters: staging -> (-0.5 z^2, z) -> bf16 hi/lo operand tiles ----------------
+    // Two groups of four warps work on ALTERNATE stages: one stage's chain (wait for z, 16 loads, split,
+    // stores, proxy fence) is ~500 cycles of latency, and with all eight warps in lockstep on one stage that
+    // latency -- not the tensor pipe (~580 cycles of MMA per stage) -- set the stage period (measured in the
+    // role trace: converters 840 cycles per stage, MMA issuer waiting for operands).
     const int ct = tid - tc::W_CV0 * 32;   // 0..255
     const int m = ct & (tc::M - 1);        // frame inside the tile
-    const int half = ct >> 7;              // which 8-channel chunk of the stage's 16 channels
+    const int grp = ct >> 7;               // which of the two converter groups
     const int G = ntile_local * p.NCB;
-    int zs = 0, zuse = 0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = grp; g < G; g += 2) {
       const uint32_t it = static_cast<uint32_t>(g);
       const int s = it % tc::STAGES;
+      const int zs = g % p.ZS;
+      const int zuse = g / p.ZS;
       if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 0, g);
       ptx::mbar_wait(&z_full[zs], zuse & 1);
-      const float* src = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + static_cast<size_t>(half * 8) * tc::M + m;
-      float z[8];
+      if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 3, g);
+      const float* src = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + m;
+      float z[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) z[i] = src[i * tc::M];
+      for (int i = 0; i < 16; ++i) z[i] = src[i * tc::M];
       if (it >= tc::STAGES) ptx::mbar_wait(&empty[s], ((it / tc::STAGES) - 1) & 1);  // MMAs of the previous use are done
       if (warp == tc::W_CV0 && lane == 0) trace_ev(p, tsm, tcnt, 3, 1, g);
       unsigned char* a_base = smem + s * stage_bytes;
       if (!(p.dbg & 2)) {
-        const int q = 0;
-        uint32_t a2h[4], a2l[4], zh[4], zl[4];
 #pragma unroll
-        for (int i2 = 0; i2 < 4; ++i2) {
-          uint32_t h[2][4];  // [elem][a2_hi, a2_lo, z_hi, z_lo] as fp32 bit patterns
+        for (int half = 0; half < 2; ++half) {  // the two 8-channel chunks of the stage's 16 channels
+          uint32_t a2h[4], a2l[4], zh[4], zl[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float zz = z[q * 8 + i2 * 2 + e];
-            const float a2 = -0.5f * (zz * zz);  // :227
-            split_bits(a2, h[e][0], h[e][1]);
-            split_bits(zz, h[e][2], h[e][3]);
+          for (int i2 = 0; i2 < 4; ++i2) {
+            uint32_t h[2][4];  // [elem][a2_hi, a2_lo, z_hi, z_lo] as fp32 bit patterns
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float zz = z[half * 8 + i2 * 2 + e];
+              const float a2 = -0.5f * (zz * zz);  // :227
+              split_bits(a2, h[e][0], h[e][1]);
+              split_bits(zz, h[e][2], h[e][3]);
+            }
+            a2h[i2] = pack2(h[0][0], h[1][0]);
+            a2l[i2] = pack2(h[0][1], h[1][1]);
+            zh[i2] = pack2(h[0][2], h[1][2]);
+            zl[i2] = pack2(h[0][3], h[1][3]);
           }
-          a2h[i2] = pack2(h[0][0], h[1][0]);
-          a2l[i2] = pack2(h[0][1], h[1][1]);
-          zh[i2] = pack2(h[0][2], h[1][2]);
-          zl[i2] = pack2(h[0][3], h[1][3]);
+          const uint32_t off = static_cast<uint32_t>(half) * tc::A_LBO + static_cast<uint32_t>(m) * 16u;
+          *reinterpret_cast<uint4*>(a_base + 0 * tc::A_ARR + off) = make_uint4(a2h[0], a2h[1], a2h[2], a2h[3]);
+          *reinterpret_cast<uint4*>(a_base + 1 * tc::A_ARR + off) = make_uint4(a2l[0], a2l[1], a2l[2], a2l[3]);
+          *reinterpret_cast<uint4*>(a_base + 2 * tc::A_ARR + off) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+          *reinterpret_cast<uint4*>(a_base + 3 * tc::A_ARR + off) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
         }
-        const uint32_t off = static_cast<uint32_t>(half) * tc::A_LBO + static_cast<uint32_t>(m) * 16u;
-        *reinterpret_cast<uint4*>(a_base + 0 * tc::A_ARR + off) = make_uint4(a2h[0], a2h[1], a2h[2], a2h[3]);
-        *reinterpret_cast<uint4*>(a_base + 1 * tc::A_ARR + off) = make_uint4(a2l[0], a2l[1], a2l[2], a2l[3]);
-        *reinterpret_cast<uint4*>(a_base + 2 * tc::A_ARR + off) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
-        *reinterpret_cast<uint4*>(a_base + 3 * tc::A_ARR + off) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
       }
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
       __syncwarp();
@@ -570,10 +599,6 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       if (lane == 0) {
         ptx::mbar_arrive(&full[s]);
         ptx::mbar_arrive(&z_empty[zs]);  // the staging slot was fully read (values are in registers)
-      }
-      if (++zs == p.ZS) {
-        zs = 0;
-        ++zuse;
       }
     }
   }
@@ -628,7 +653,8 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   float* bias = reinterpret_cast<float*>(bops + ((s.bops_bytes + 255) & ~size_t(255)));
 
   PrepParams pp{m_p, logs_p, bops, bias, B, C, T_x, s.Nt, s.NTL, s.NCB};
-  neg_cent_prep_kernel<<<dim3(s.NTL, B, s.NPB), s.Nt, 0, st>>>(pp);  // 4 chunks x Nt/4 column quads
+  static const int g_dbg = getenv("MAS_NC_DEBUG") ? atoi(getenv("MAS_NC_DEBUG")) : 0;
+  if (!(g_dbg & 256)) neg_cent_prep_kernel<<<dim3(s.NTL * (s.Nt / 16), B, s.NPB), 64, 0, st>>>(pp);  // 4 chunks x 16 columns
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
@@ -673,6 +699,7 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   la[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = la;
   cfg.numAttrs = 1;
+  if (tp.dbg & 128) return MAS_OK;
   e = cudaLaunchKernelEx(&cfg, neg_cent_tc_kernel, tp);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
