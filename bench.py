@@ -351,8 +351,13 @@ def run_ours(args, rank, world, local_rank):
         h_vals = [torch.empty(B, T_y, T_x, dtype=torch.float32).pin_memory() for _ in range(2)]
         for hv, nc in zip(h_vals, ncs):
             hv.copy_(nc)
-        h_paths = [torch.empty(B, T_y, T_x, dtype=torch.int32).pin_memory() for _ in range(2)]
+        # zero-filled once, as the reference's caller does (np.zeros, __init__.py:15): the entry writes every
+        # row below t_y_i in full and, like core.pyx, never touches the padded rows
+        h_paths = [torch.zeros(B, T_y, T_x, dtype=torch.int32).pin_memory() for _ in range(2)]
         h_ty, h_tx = torch.as_tensor(t_ys), torch.as_tensor(t_xs)
+        ty_np = np.clip(np.asarray(t_ys), 0, T_y)
+        per = -(-B // min(B, 16))  # utterances per internal group of the host entry (16 groups)
+        valid_row_bytes = int(4 * T_x * sum(int(ty_np[b0:b0 + per].max()) * len(ty_np[b0:b0 + per]) for b0 in range(0, B, per)))
 
         def host_step(i):
             rc = L.mas_maximum_path_c_host(h_paths[i % 2].data_ptr(), h_vals[i % 2].data_ptr(), h_ty.data_ptr(),
@@ -368,12 +373,34 @@ def run_ours(args, rank, world, local_rank):
         td = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        # the link itself, for scale: one plain pinned copy of a whole [B,T_y,T_x] plane each way
+        link = None
+        if rank == 0:
+            d_tmp = torch.empty(B, T_y, T_x, dtype=torch.float32, device=dev)
+            gbs = []
+            for src, dst in ((h_vals[0], d_tmp), (d_tmp, h_vals[1])):
+                dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                for _ in range(5):
+                    dst.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+                gbs.append(5 * plane_bytes / (time.perf_counter() - t1) / 1e9)
+            h_vals[1].copy_(ncs[1 % len(ncs)])
+            link = {"h2d_gbs": gbs[0], "d2h_gbs": gbs[1],
+                    "one_way_bound": B / (valid_row_bytes / (min(gbs) * 1e9)),
+                    "note": "pinned cudaMemcpy of one 50 MB plane; one_way_bound = alignments/s if a step cost only "
+                            "its slower copy direction at that rate (both directions overlap in the entry)"}
+            del d_tmp
         if rank == 0:
             from oracle import mas_oracle
             want = mas_oracle.maximum_path_numpy(h_vals[0].numpy(), t_ys, t_xs)
             assert np.array_equal(h_paths[0].numpy(), want), "e2e path differs from the oracle"
         e2e = {"value": world * B * e2e_steps / float(td.item()), "unit": UNIT,
-               "h2d_bytes_per_step": plane_bytes + 8 * B, "d2h_bytes_per_step": plane_bytes + 32,
+               "h2d_bytes_per_step": valid_row_bytes + 8 * B, "d2h_bytes_per_step": valid_row_bytes + 64,
+               "copied": "leading rows of every utterance up to the longest of its group of 4, both directions (the "
+                         "padded tail is never needed, as in core.pyx:13-33); host paths buffer zero-filled once",
+               "pcie_link": link,
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",
                "api": "mas_maximum_path_c_host (twin of core.pyx:38), pinned host buffers"}
         L.mas_host_release()

@@ -90,7 +90,11 @@ int mas_maximum_path(const float* neg_cent,
  * `maximum_path_c(int[:,:,::1] paths, float[:,:,::1] values, int[::1] t_ys, int[::1] t_xs)`
  * (core.pyx:38) with HOST pointers: copies values to the device, runs mas_maximum_path, copies
  * the int32 paths back, and synchronises.  `values` is left untouched (the reference clobbers
- * its host copy; nothing reads it afterwards, __init__.py:19-20).  Uses an internal stream and
+ * its host copy; nothing reads it afterwards, __init__.py:19-20).  Like the reference, which loops
+ * over the first t_ys[b] rows of a caller-zeroed `paths` (core.pyx:13-33, __init__.py:15), rows
+ * y >= t_ys[b] need not be read from `values` nor written to `paths` (the padded tail is skipped up to
+ * the longest utterance of each internal group; what is written there is zeros): pass `paths`
+ * zero-filled, as np.zeros does.  Rows below t_ys[b] are written in full (zeros and ones).  Uses internal streams and
  * cached device/pinned buffers; not re-entrant (the reference has a single caller thread).
  * Returns 0, a MAS_E_* code, or MAS_STATUS_* bits << 8 when an utterance had invalid lengths.
  */

@@ -292,11 +292,20 @@ def test_host_buffer_entry_matches_maximum_path_c(mp, oracle):
         values = rng.standard_normal((B, T_y, T_x)).astype(np.float32)
         keep = values.copy()
         t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
-        paths = np.full((B, T_y, T_x), 9, dtype=np.int32)
+        paths = np.zeros((B, T_y, T_x), dtype=np.int32)  # the caller zeroes it, __init__.py:15
         rc = L.mas_maximum_path_c_host(paths.ctypes.data, values.ctypes.data, t_ys.ctypes.data, t_xs.ctypes.data, B, T_y, T_x)
         assert rc == 0
-        np.testing.assert_array_equal(paths, oracle.maximum_path_numpy(keep, t_ys, t_xs))
+        want = oracle.maximum_path_numpy(keep, t_ys, t_xs)
+        np.testing.assert_array_equal(paths, want)
         np.testing.assert_array_equal(values, keep)
+        # rows below t_y are written in full; rows at or beyond it are either left alone (like core.pyx:13-33)
+        # or zeroed, and nothing beyond the longest utterance is touched
+        dirty = np.full((B, T_y, T_x), 9, dtype=np.int32)
+        assert L.mas_maximum_path_c_host(dirty.ctypes.data, values.ctypes.data, t_ys.ctypes.data, t_xs.ctypes.data, B, T_y, T_x) == 0
+        for b in range(B):
+            np.testing.assert_array_equal(dirty[b, :t_ys[b]], want[b, :t_ys[b]])
+            assert np.isin(dirty[b, t_ys[b]:], (0, 9)).all()
+            assert (dirty[b, t_ys.max():] == 9).all()
         nc_cpu = torch.from_numpy(values)
         out = mp.maximum_path(nc_cpu, _mask(t_ys, t_xs, T_y, T_x, "cpu"))
         assert out.device.type == "cpu" and out.dtype == torch.float32

@@ -24,6 +24,7 @@ struct HostCtx {
   void* d_paths = nullptr;
   void* d_lens = nullptr;
   void* d_scratch = nullptr;
+  cudaEvent_t ev_in[kChunks] = {}, ev_k[kChunks] = {};  // group c: inputs landed / kernels done
   int32_t* h_status = nullptr;  // pinned, kChunks words
   size_t cap_cells = 0, cap_lens = 0, cap_scratch = 0;
   bool ready = false;
@@ -37,6 +38,10 @@ void host_release() {
   if (g_host.h_status) cudaFreeHost(g_host.h_status);
   for (auto& s : g_host.streams)
     if (s) cudaStreamDestroy(s);
+  for (auto& e : g_host.ev_in)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : g_host.ev_k)
+    if (e) cudaEventDestroy(e);
   g_host = HostCtx{};
 }
 
@@ -49,6 +54,8 @@ void host_release() {
 int host_prepare(size_t cells, size_t lens, size_t scratch) {
   if (!g_host.ready) {
     for (auto& s : g_host.streams) MAS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : g_host.ev_in) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_host.ev_k) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MAS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_host.h_status), HostCtx::kChunks * sizeof(int32_t),
                            cudaHostAllocDefault));
     g_host.ready = true;
@@ -109,6 +116,25 @@ int mas_maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* 
                            index_out, scratch, scratch_bytes, B, T_y, T_x, static_cast<cudaStream_t>(stream));
 }
 
+// Copies the leading rows of utterances [b0, b0+nb) (4-byte cells, planes of T_y*T_x) up to the group's
+// longest utterance, as ONE strided copy: the reference never touches a row at or beyond an utterance's
+// length (core.pyx:13-33 loops over t_y rows of a caller-zeroed `paths`), so the padded tail is neither
+// sent nor read back.  Batches arrive sorted by length (TextAudioSpeakerCollate.py:26-30), so a group's
+// utterances are about equally long.  (One copy per utterance moved fewer bytes but was slower: 128 small
+// copies per call cost more host time than the PCIe time they saved.)
+static cudaError_t copy_leading_rows(void* dst, const void* src, const int32_t* t_ys, int b0, int nb, int T_y, int T_x,
+                                     cudaMemcpyKind kind, cudaStream_t st) {
+  const size_t plane = static_cast<size_t>(T_y) * T_x * 4;
+  int rows = 0;
+  for (int b = b0; b < b0 + nb; ++b) rows = t_ys[b] > rows ? t_ys[b] : rows;
+  rows = rows > T_y ? T_y : rows;
+  if (rows <= 0) return cudaSuccess;
+  char* d = static_cast<char*>(dst) + plane * b0;
+  const char* s = static_cast<const char*>(src) + plane * b0;
+  if (rows == T_y) return cudaMemcpyAsync(d, s, plane * nb, kind, st);
+  return cudaMemcpy2DAsync(d, plane, s, plane, static_cast<size_t>(rows) * T_x * 4, nb, kind, st);
+}
+
 int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs, int B,
                             int T_y, int T_x) {
   if (B <= 0 || T_y <= 0 || T_x <= 0) return MAS_E_BAD_SHAPE;
@@ -125,36 +151,37 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
   int32_t* d_paths = static_cast<int32_t*>(g_host.d_paths);
   int32_t* d_ty = static_cast<int32_t*>(g_host.d_lens);
   int32_t* d_tx = d_ty + B;
-  cudaStream_t s0 = g_host.streams[0];
-  MAS_CUDA(cudaMemcpyAsync(d_ty, t_ys, B * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
-  MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s0));
-  MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * nch, s0));
-  cudaEvent_t ready;
-  MAS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  MAS_CUDA(cudaEventRecord(ready, s0));
-  for (int i = 1; i < HostCtx::kStreams; ++i) MAS_CUDA(cudaStreamWaitEvent(g_host.streams[i], ready, 0));
-
-  // utterance groups: H2D -> kernels -> D2H, round-robin over the streams so the copies of one
-  // group overlap the kernels / opposite-direction copies of its neighbours.
+  // One stream feeds the inputs group by group without ever waiting for anything (H2D copy engine busy
+  // from the first byte to the last), two streams run the kernels of alternate groups, one stream returns
+  // the paths (D2H copy engine); events hand each group from stage to stage.  (With whole groups
+  // round-robined over four streams, a stream's next H2D queued behind its previous D2H and the inbound
+  // engine idled: 1.41 ms per c2 call for 2 x 50 MB.)
+  cudaStream_t s_in = g_host.streams[0], s_out = g_host.streams[3];
+  MAS_CUDA(cudaMemcpyAsync(d_ty, t_ys, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
+  MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
+  MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * nch, s_in));
   int nused = 0;
   for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
     const int nb = (B - b0) < per ? (B - b0) : per;
-    cudaStream_t st = g_host.streams[c % HostCtx::kStreams];
+    cudaStream_t s_k = g_host.streams[1 + (c & 1)];
     unsigned char* sc = static_cast<unsigned char*>(g_host.d_scratch) + sc_one * c;
-    MAS_CUDA(cudaMemcpyAsync(d_values + plane * b0, values + plane * b0, plane * nb * 4, cudaMemcpyHostToDevice, st));
+    MAS_CUDA(copy_leading_rows(d_values, values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
+    MAS_CUDA(cudaEventRecord(g_host.ev_in[c], s_in));
+    MAS_CUDA(cudaStreamWaitEvent(s_k, g_host.ev_in[c], 0));
     rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0,
-                           MAS_I32, nullptr, sc, sc_one, nb, T_y, T_x, st);
+                           MAS_I32, nullptr, sc, sc_one, nb, T_y, T_x, s_k);
     if (rc != MAS_OK) {
-      cudaEventDestroy(ready);
+      for (auto& s : g_host.streams) cudaStreamSynchronize(s);
       return rc;
     }
-    MAS_CUDA(cudaMemcpyAsync(paths + plane * b0, d_paths + plane * b0, plane * nb * 4, cudaMemcpyDeviceToHost, st));
+    MAS_CUDA(cudaEventRecord(g_host.ev_k[c], s_k));
+    MAS_CUDA(cudaStreamWaitEvent(s_out, g_host.ev_k[c], 0));
+    MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out));
     MAS_CUDA(cudaMemcpyAsync(&g_host.h_status[c], sc + mas_scratch_status_offset(), sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, st));
+                             cudaMemcpyDeviceToHost, s_out));
     nused = c + 1;
   }
   for (auto& s : g_host.streams) MAS_CUDA(cudaStreamSynchronize(s));
-  cudaEventDestroy(ready);
   int status = 0;
   for (int c = 0; c < nused; ++c) status |= g_host.h_status[c];
   return status ? (status << 8) : MAS_OK;

@@ -148,7 +148,7 @@ def _run_host(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch.Tensor, ch
         values = values.float()
     t_ys = t_ys.to(torch.int32).contiguous()
     t_xs = t_xs.to(torch.int32).contiguous()
-    paths = torch.empty((B, T_y, T_x), dtype=torch.int32)
+    paths = torch.zeros((B, T_y, T_x), dtype=torch.int32)  # np.zeros, __init__.py:15: padded rows are never written
     rc = L.mas_maximum_path_c_host(paths.data_ptr(), values.data_ptr(), t_ys.data_ptr(), t_xs.data_ptr(), B, T_y, T_x)
     if rc > 0 and (rc & 0xFF) == 0:
         if check or _CHECK:
