@@ -85,6 +85,36 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_entry_groups(B, plane_bytes):
+    """(first utterance, count) of the groups mas_maximum_path_c_host pipelines over PCIe (mas_api.cu): about
+    12 MB each, the first and last a quarter of that.  Only used to count the bytes the entry copies."""
+    groups = min(B, max(2, min(16, (plane_bytes + (6 << 20)) // (12 << 20))))
+    per = -(-B // groups)
+    q = per // 4 if per >= 4 else 0
+    sizes, left = [], B
+
+    def push(n):
+        nonlocal left
+        n = min(n, left)
+        if n > 0:
+            sizes.append(n)
+            left -= n
+    if q:
+        push(q)
+        push(per - q)
+        while left > per:
+            push(per)
+        push(left - q)
+        push(q)
+    while left > 0:
+        push(per)
+    out, b0 = [], 0
+    for n in sizes:
+        out.append((b0, n))
+        b0 += n
+    return out
+
+
 def make_lengths(rng, B, T_y, T_x, ragged):
     if not ragged:
         return np.full(B, T_y, np.int32), np.full(B, T_x, np.int32)
@@ -356,8 +386,7 @@ def run_ours(args, rank, world, local_rank):
         h_paths = [torch.zeros(B, T_y, T_x, dtype=torch.int32).pin_memory() for _ in range(2)]
         h_ty, h_tx = torch.as_tensor(t_ys), torch.as_tensor(t_xs)
         ty_np = np.clip(np.asarray(t_ys), 0, T_y)
-        per = -(-B // min(B, 16))  # utterances per internal group of the host entry (16 groups)
-        valid_row_bytes = int(4 * T_x * sum(int(ty_np[b0:b0 + per].max()) * len(ty_np[b0:b0 + per]) for b0 in range(0, B, per)))
+        valid_row_bytes = int(4 * T_x * sum(int(ty_np[b0:b0 + n].max()) * n for b0, n in host_entry_groups(B, plane_bytes)))
 
         def host_step(i):
             rc = L.mas_maximum_path_c_host(h_paths[i % 2].data_ptr(), h_vals[i % 2].data_ptr(), h_ty.data_ptr(),
@@ -386,19 +415,33 @@ def run_ours(args, rank, world, local_rank):
                     dst.copy_(src, non_blocking=True)
                 torch.cuda.synchronize()
                 gbs.append(5 * plane_bytes / (time.perf_counter() - t1) / 1e9)
+            d_tmp2 = torch.empty_like(d_tmp)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def both(n):
+                for _ in range(n):
+                    with torch.cuda.stream(s1):
+                        d_tmp.copy_(h_vals[0], non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        h_vals[1].copy_(d_tmp2, non_blocking=True)
+                torch.cuda.synchronize()
+            both(1)
+            t1 = time.perf_counter()
+            both(5)
+            duplex_s = (time.perf_counter() - t1) / 5
             h_vals[1].copy_(ncs[1 % len(ncs)])
-            link = {"h2d_gbs": gbs[0], "d2h_gbs": gbs[1],
-                    "one_way_bound": B / (valid_row_bytes / (min(gbs) * 1e9)),
-                    "note": "pinned cudaMemcpy of one 50 MB plane; one_way_bound = alignments/s if a step cost only "
-                            "its slower copy direction at that rate (both directions overlap in the entry)"}
-            del d_tmp
+            link = {"h2d_gbs": gbs[0], "d2h_gbs": gbs[1], "duplex_gbs": 2 * plane_bytes / duplex_s / 1e9,
+                    "duplex_bound": B / (duplex_s * valid_row_bytes / plane_bytes),
+                    "note": "pinned cudaMemcpy of one whole plane each way, alone and then both at once; duplex_bound = "
+                            "alignments/s if a step cost exactly its two copies at the both-at-once rate"}
+            del d_tmp, d_tmp2
         if rank == 0:
             from oracle import mas_oracle
             want = mas_oracle.maximum_path_numpy(h_vals[0].numpy(), t_ys, t_xs)
             assert np.array_equal(h_paths[0].numpy(), want), "e2e path differs from the oracle"
         e2e = {"value": world * B * e2e_steps / float(td.item()), "unit": UNIT,
                "h2d_bytes_per_step": valid_row_bytes + 8 * B, "d2h_bytes_per_step": valid_row_bytes + 64,
-               "copied": "leading rows of every utterance up to the longest of its group of 4, both directions (the "
+               "copied": "leading rows of every utterance up to the longest of its group, both directions (the "
                          "padded tail is never needed, as in core.pyx:13-33); host paths buffer zero-filled once",
                "pcie_link": link,
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",

@@ -11,3 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
   python bench.py --steps 8 --warmup 3 --no-graph --no-e2e --no-cpu > $out/${tag}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:mas_dp_kernel -s 2 -c 1 -f -o $out/${tag}_fwd_full \
   python tools/prof_one.py c2 > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:neg_cent_tc_kernel -s 1 -c 1 -f -o $out/${tag}_nc_full \
+  python tools/trace_nc.py > $out/${tag}_ncu_nc_full.log 2>&1; echo "ncu neg_cent full rc=$?"

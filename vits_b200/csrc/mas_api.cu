@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/vits_mas.h"
@@ -17,7 +18,7 @@ namespace {
 
 // State cached by the host entry (single caller thread, like the reference).
 struct HostCtx {
-  static constexpr int kChunks = 16;  // utterance groups pipelined over PCIe
+  static constexpr int kChunks = 32;  // most utterance groups pipelined over PCIe
   static constexpr int kStreams = 4;
   cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr, nullptr};
   void* d_values = nullptr;
@@ -140,11 +141,48 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
   if (B <= 0 || T_y <= 0 || T_x <= 0) return MAS_E_BAD_SHAPE;
   if (!paths || !values || !t_ys || !t_xs) return MAS_E_NULL;
   const size_t plane = static_cast<size_t>(T_y) * T_x;
-  const int nch = B < HostCtx::kChunks ? B : HostCtx::kChunks;
+  // Groups of about 12 MB: enough of them to overlap the two copy directions and the kernels, few enough
+  // that the ~11 driver calls per group stay off the critical path (c2, 2 x 50 MB: 4 groups 46.4k
+  // alignments/s full-length, 8 groups 44.5k, 16 groups 38.3k; the duplex link bound is 59.5k).
+  static const int forced_groups = [] {
+    const char* e = getenv("MAS_HOST_GROUPS");  // tuning hook
+    const int v = e ? atoi(e) : 0;
+    return v > 0 && v <= HostCtx::kChunks - 2 ? v : 0;
+  }();
+  int want_chunks = forced_groups;
+  if (!want_chunks) {
+    const size_t total = plane * B * 4, target = size_t(12) << 20;
+    want_chunks = static_cast<int>((total + target / 2) / target);
+    want_chunks = want_chunks < 2 ? 2 : (want_chunks > 16 ? 16 : want_chunks);
+  }
+  const int nch = B < want_chunks ? B : want_chunks;
   const int per = (B + nch - 1) / nch;
+  // Tapered groups: the first inbound and the last outbound copy run with the other direction idle, so the
+  // first and last group are a quarter of the nominal size (c2: 4, 12, 16, 16, 12, 4 utterances).
+  int gsize[HostCtx::kChunks];
+  int ng = 0;
+  {
+    const int q = per >= 4 ? per / 4 : 0;
+    int left = B;
+    auto push = [&](int n) {
+      n = n < left ? n : left;
+      if (n > 0) {
+        gsize[ng++] = n;
+        left -= n;
+      }
+    };
+    if (q && !getenv("MAS_HOST_FLAT")) {
+      push(q);
+      push(per - q);
+      while (left > per) push(per);
+      push(left - q);
+      push(q);
+    }
+    while (left > 0) push(per);
+  }
   const size_t sc_one = (mas::maximum_path_scratch_bytes(per, T_y, T_x) + 255) & ~size_t(255);
   if (sc_one == 0) return MAS_E_BAD_SHAPE;
-  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * nch);
+  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * ng);
   if (rc != MAS_OK) return rc;
 
   float* d_values = static_cast<float*>(g_host.d_values);
@@ -159,10 +197,10 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
   cudaStream_t s_in = g_host.streams[0], s_out = g_host.streams[3];
   MAS_CUDA(cudaMemcpyAsync(d_ty, t_ys, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
   MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
-  MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * nch, s_in));
+  MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * ng, s_in));
   int nused = 0;
-  for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
-    const int nb = (B - b0) < per ? (B - b0) : per;
+  for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
+    const int nb = gsize[c];
     cudaStream_t s_k = g_host.streams[1 + (c & 1)];
     unsigned char* sc = static_cast<unsigned char*>(g_host.d_scratch) + sc_one * c;
     MAS_CUDA(copy_leading_rows(d_values, values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
@@ -177,10 +215,12 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
     MAS_CUDA(cudaEventRecord(g_host.ev_k[c], s_k));
     MAS_CUDA(cudaStreamWaitEvent(s_out, g_host.ev_k[c], 0));
     MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out));
-    MAS_CUDA(cudaMemcpyAsync(&g_host.h_status[c], sc + mas_scratch_status_offset(), sizeof(int32_t),
-                             cudaMemcpyDeviceToHost, s_out));
     nused = c + 1;
   }
+  // the status word of every group (first word of its scratch) in one strided copy
+  MAS_CUDA(cudaMemcpy2DAsync(g_host.h_status, sizeof(int32_t),
+                             static_cast<unsigned char*>(g_host.d_scratch) + mas_scratch_status_offset(), sc_one,
+                             sizeof(int32_t), nused, cudaMemcpyDeviceToHost, s_out));
   for (auto& s : g_host.streams) MAS_CUDA(cudaStreamSynchronize(s));
   int status = 0;
   for (int c = 0; c < nused; ++c) status |= g_host.h_status[c];
