@@ -131,6 +131,9 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
     built with its setup.py's flags => serial) through the wrapper's marshalling; R2: core only;
     R4: the same Cython rebuilt with -O3 -fopenmp on all cores (steelman)."""
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference's wrapper (torch/numpy marshalling around the serial
+    # Cython core) gets every host thread it can use, whatever launched us
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     from oracle import mas_oracle
     stock = mas_oracle.load_ref_core("stock")
     omp = mas_oracle.load_ref_core("omp")
@@ -236,6 +239,7 @@ def run_reference(args, rank, world):
                    "path": "monotonic_align.maximum_path wrapper marshalling (__init__.py:14-20) + the reference's "
                            "compiled core.pyx, built with its setup.py's flags (no OpenMP => serial prange)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "torch_threads": torch.get_num_threads(),
                          "sample": f"{steps} full batches of the workload", "variants": extra, "host": host},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
