@@ -475,6 +475,19 @@ def run_ours(args, rank, world, local_rank):
         other = {"workload": "full-length" if primary_ragged else "ragged lengths", "value": O["value"], "unit": UNIT,
                  "ms_per_step": O["step_ms"], "steps": max(20, args.steps // 4),
                  "roofline_frac": O["alg_bytes"] / (O["step_ms"] * 1e-3) / 1e9 / peak, "parity_checked": O["parity"]}
+        # DRAM bytes of one step's three kernels from `ncu --set full` (profiles/): only captured for c2, B = 64
+        traffic, traffic_note = None, "not captured for this workload"
+        if args.workload == "c2" and primary_ragged:
+            traffic = 43.77e6 + 50.33e6
+            traffic_note = ("c2 variable lengths, profiles/r01_g_chain_c2_variable_lengths.ncu-rep: dram read+write inside the "
+                            "kernels' windows = mas_dp 40.79 MB (30.6 MB algorithmic: 32x64 TMA boxes overhang the band "
+                            "and t_x) + mas_writeout 0.87 MB + mas_backtrack_stream 2.11 MB = 43.77 MB, plus the 50.33 MB "
+                            "dense path that ncu sees absorbed by the 126 MB L2 and that is written back after the "
+                            "window (counted here once, as it must reach HBM)")
+        elif args.workload == "c2":
+            traffic = 105.4e6
+            traffic_note = ("full-length c2, profiles/r01_f_mas_dp_summary.txt: mas_dp 50.4 MB DRAM read + 1.6 MB of tagged "
+                            "decision words (and 3.1 MB of tag clears), mas_writeout 50.3 MB written")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -489,7 +502,8 @@ def run_ours(args, rank, world, local_rank):
                        "parity_checked": parity, "multi_gpu_verified": verified},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "path_breakdown": breakdown,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (105.4e6 if not primary_ragged else None), "traffic_note": "full-length c2, ncu --set full (profiles/): mas_dp 50.4 MB DRAM read + 1.6 MB of tagged decision words written (and 3.1 MB of tag clears), mas_writeout 50.3 MB written; not captured for the variable-length variant", "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes,
+                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg_bytes,
                          "kernel": "maximum_path chain (mas_dp wavefront forward kernel + mas_writeout zero-fill + "
                                    "mas_backtrack_stream, concurrent on disjoint SMs through programmatic dependent launch, "
                                    "timed as one unit with CUDA events on the launching stream)",
