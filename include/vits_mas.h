@@ -119,6 +119,18 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                  int B, int C, int T_y, int T_x, mas_stream_t stream);
 
 /*
+ * mas_neg_cent_autocast -- the same contraction with the numerics the reference has AS TRAINED, inside
+ * torch.autocast (train_and_evaluate.py:55, config_cje.yaml:11 fp16_run): the two einsums
+ * (SynthesizerTrn.py:227, :229) take their operands rounded to `gemm_dtype` (MAS_F16 or MAS_BF16),
+ * accumulate in fp32 and round each einsum's output to `gemm_dtype`; exp, pow and the channel sums
+ * (:223, :225, :231) stay fp32; the four terms are added in fp32 left to right (:232).  Inputs and the
+ * result are float32 as in mas_neg_cent.  A parity mode on CUDA cores, not a fast path; mas_neg_cent is
+ * the fp32 formulation and the default.
+ */
+int mas_neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent,
+                          int gemm_dtype, int B, int C, int T_y, int T_x, mas_stream_t stream);
+
+/*
  * Callers either side of the path.  All pointers are device pointers, fp32 contiguous
  * unless strides are given; asynchronous on `stream`.
  *

@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star / SURVEY.md 8d):
   * end-to-end: >= 99.9 % of path cells equal the oracle's, every differing frame a near-tie.
 """
 import numpy as np
+import math
+
 import pytest
 import torch
 
@@ -68,6 +70,47 @@ def test_neg_cent_ignores_autocast(oracle):
     with torch.autocast("cuda", dtype=torch.float16):
         ours = vits_b200.neg_cent(z.half(), m, ls)
     _check(ours, oracle.neg_cent_torch(z.half().float(), m, ls))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 192, 260, 90), (2, 192, 129, 65), (8, 192, 512, 192)])
+def test_neg_cent_autocast_parity_mode(oracle, dtype, shape):
+    """the contraction with the numerics the reference has AS TRAINED.  The
+    target is the literal expression (SynthesizerTrn.py:223-232) run under torch.autocast on the GPU: both
+    einsums on low-precision operands with low-precision outputs, everything else fp32.  cuBLAS and our kernel
+    add the fp32 partial products in a different order, so an einsum output may land on the other side of a
+    rounding boundary: nearly all elements must be EQUAL, none further away than one ulp per einsum term, and
+    the fp32 formulation (the default mode) must be clearly distinguishable from it."""
+    import vits_b200
+    z, m, ls = _inputs(*shape, seed=17)
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype):   # oracle.neg_cent_torch switches autocast off: spell it out
+        inv_var = torch.exp(-2 * ls)                                                        # :223
+        want = (torch.sum(-0.5 * math.log(2 * math.pi) - ls, [1], keepdim=True)             # :225
+                + torch.einsum("bdt, bds -> bts", -0.5 * (z ** 2), inv_var)                 # :227
+                + torch.einsum("bdt, bds -> bts", z, m * inv_var)                           # :229
+                + torch.sum(-0.5 * (m ** 2) * inv_var, [1], keepdim=True))                  # :231, :232
+    assert want.dtype == torch.float32
+    got = vits_b200.neg_cent(z, m, ls, autocast_dtype=dtype)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    eps = torch.finfo(dtype).eps
+    with torch.autocast("cuda", dtype=dtype):   # magnitude of the two rounded terms
+        s = torch.exp(-2 * ls)
+        t2 = torch.einsum('bdt,bds->bts', -0.5 * z ** 2, s).float().abs().max().item()
+        t3 = torch.einsum('bdt,bds->bts', z, m * s).float().abs().max().item()
+    bound = eps * (t2 + t3) + 1e-4 * want.abs().max().item()
+    diff = (got - want).abs()
+    assert diff.max().item() <= bound, (diff.max().item(), bound)
+    equal = (diff <= 2e-6 * want.abs().max()).float().mean().item()   # fp32 sums of terms 1 and 4 may differ in the last bit
+    assert equal >= 0.9, equal
+    fp32_mode = vits_b200.neg_cent(z, m, ls)
+    assert ((fp32_mode - want).abs() <= 2e-6 * want.abs().max()).float().mean().item() < 0.5
+
+
+def test_neg_cent_autocast_mode_rejects_other_types():
+    import vits_b200
+    z, m, ls = _inputs(1, 192, 64, 32, seed=1)
+    with pytest.raises(ValueError):
+        vits_b200.neg_cent(z, m, ls, autocast_dtype=torch.float64)
 
 
 @pytest.mark.parametrize("shape", [(8, 192, 400, 100), (64, 192, 1024, 192)])

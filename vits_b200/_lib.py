@@ -19,7 +19,7 @@ MAS_STATUS_TX_GT_TY, MAS_STATUS_EMPTY, MAS_STATUS_TOO_LONG = 1, 2, 4
 EXPORTS = [
     "mas_abi_version", "mas_error_string", "mas_maximum_path_scratch_bytes", "mas_scratch_status_offset",
     "mas_maximum_path", "mas_maximum_path_c_host", "mas_host_release", "mas_neg_cent_scratch_bytes",
-    "mas_neg_cent", "mas_path_durations", "mas_expand_prior", "mas_generate_path", "mas_kl_from_index", "mas_launch_count", "mas_set_tuning", "mas_set_neg_cent_impl", "mas_set_debug_kernels", "mas_set_tuning2", "mas_set_tuning3", "mas_set_timeline", "mas_set_trace",
+    "mas_neg_cent", "mas_neg_cent_autocast", "mas_path_durations", "mas_expand_prior", "mas_generate_path", "mas_kl_from_index", "mas_launch_count", "mas_set_tuning", "mas_set_neg_cent_impl", "mas_set_debug_kernels", "mas_set_tuning2", "mas_set_tuning3", "mas_set_timeline", "mas_set_trace",
 ]
 
 
@@ -63,6 +63,8 @@ def lib() -> ctypes.CDLL:
     L.mas_launch_count.restype = ctypes.c_uint64
     L.mas_set_tuning.restype = None
     L.mas_set_tuning.argtypes = [c_int, c_int, c_int, c_int]
+    L.mas_neg_cent_autocast.restype = c_int
+    L.mas_neg_cent_autocast.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]
     L.mas_set_neg_cent_impl.restype = None
     L.mas_set_neg_cent_impl.argtypes = [c_int]
     L.mas_set_debug_kernels.restype = None

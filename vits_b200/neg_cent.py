@@ -3,7 +3,7 @@
 (include/vits_mas.h).  fp32 in, fp32 out, independent of any surrounding autocast context."""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -21,11 +21,17 @@ def _scratch_for(device: torch.device, stream: int, nbytes: int) -> torch.Tensor
     return buf
 
 
-def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torch.Tensor:
+def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor, *,
+             autocast_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """z_p [B,C,T_y]; m_p, logs_p [B,C,T_x]  ->  neg_cent [B,T_y,T_x] float32.
 
     Inputs of other float dtypes (e.g. fp16 activations under autocast) are promoted to float32
-    first: the parity target is the reference's fp32 formulation."""
+    first: the parity target is the reference's fp32 formulation.
+
+    ``autocast_dtype=torch.float16`` (or ``bfloat16``) selects the autocast-parity mode instead: the numerics
+    the reference has as trained under ``autocast(fp16_run)`` (train_and_evaluate.py:55) -- both einsums on
+    operands rounded to that type with their outputs rounded to it, everything else fp32.  It runs on CUDA
+    cores and is there to reproduce as-trained alignments, not for speed."""
     if not (z_p.is_cuda and m_p.is_cuda and logs_p.is_cuda):
         raise ValueError("neg_cent needs CUDA tensors (there is no CPU implementation)")
     if z_p.dim() != 3 or m_p.dim() != 3 or m_p.shape != logs_p.shape or z_p.shape[:2] != m_p.shape[:2]:
@@ -38,6 +44,13 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor) -> torc
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         out = torch.empty((B, T_y, T_x), dtype=torch.float32, device=dev)
+        if autocast_dtype is not None:
+            code = {torch.float16: 1, torch.bfloat16: 2}.get(autocast_dtype)
+            if code is None:
+                raise ValueError("autocast_dtype must be torch.float16 or torch.bfloat16")
+            rc = L.mas_neg_cent_autocast(z.data_ptr(), m.data_ptr(), ls.data_ptr(), out.data_ptr(), code, B, C, T_y, T_x, stream)
+            _lib.check(rc, "mas_neg_cent_autocast")
+            return out
         nbytes = int(L.mas_neg_cent_scratch_bytes(B, C, T_y, T_x))
         scratch = _scratch_for(dev, stream, nbytes)
         rc = L.mas_neg_cent(z.data_ptr(), m.data_ptr(), ls.data_ptr(), out.data_ptr(), scratch.data_ptr(),
