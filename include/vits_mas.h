@@ -124,11 +124,14 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
  * (SynthesizerTrn.py:227, :229) take their operands rounded to `gemm_dtype` (MAS_F16 or MAS_BF16),
  * accumulate in fp32 and round each einsum's output to `gemm_dtype`; exp, pow and the channel sums
  * (:223, :225, :231) stay fp32; the four terms are added in fp32 left to right (:232).  Inputs and the
- * result are float32 as in mas_neg_cent.  A parity mode on CUDA cores, not a fast path; mas_neg_cent is
- * the fp32 formulation and the default.
+ * result are float32 as in mas_neg_cent.  `stats_lowp` != 0 says that logs_p was a `gemm_dtype` tensor
+ * before the caller widened it (TextEncoder.proj returns that type under autocast, TextEncoder.py:101-104):
+ * the elementwise part of :225 then ran in that type, so every (-0.5 log 2pi - logs_p) is rounded to it
+ * before the fp32 sum.  A parity mode on CUDA cores, not a fast path; mas_neg_cent is the fp32 formulation
+ * and the default.
  */
 int mas_neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent,
-                          int gemm_dtype, int B, int C, int T_y, int T_x, mas_stream_t stream);
+                          int gemm_dtype, int stats_lowp, int B, int C, int T_y, int T_x, mas_stream_t stream);
 
 /*
  * Callers either side of the path.  All pointers are device pointers, fp32 contiguous

@@ -106,6 +106,35 @@ def test_neg_cent_autocast_parity_mode(oracle, dtype, shape):
     assert ((fp32_mode - want).abs() <= 2e-6 * want.abs().max()).float().mean().item() < 0.5
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_neg_cent_autocast_low_precision_stats(oracle, dtype):
+    """As in training: TextEncoder.proj hands m_p / logs_p over in the autocast dtype (TextEncoder.py:101-104), so
+    the elementwise part of :225 is rounded to it.  Three-way: kernel vs the literal expression under CUDA
+    autocast vs the numpy restatement (which pins the oracle's stats_lowp variant, see its docstring)."""
+    import vits_b200
+    z, m, ls = _inputs(3, 192, 200, 77, seed=23)
+    m, ls = m.to(dtype), ls.to(dtype)
+    with torch.no_grad(), torch.autocast("cuda", dtype=dtype):
+        inv_var = torch.exp(-2 * ls)
+        assert inv_var.dtype == torch.float32
+        e1 = -0.5 * math.log(2 * math.pi) - ls
+        assert e1.dtype == dtype
+        want = (torch.sum(e1, [1], keepdim=True)
+                + torch.einsum("bdt, bds -> bts", -0.5 * (z ** 2), inv_var)
+                + torch.einsum("bdt, bds -> bts", z, m * inv_var)
+                + torch.sum(-0.5 * (m ** 2) * inv_var, [1], keepdim=True))
+    assert want.dtype == torch.float32
+    got = vits_b200.neg_cent(z, m, ls, autocast_dtype=dtype)
+    rest = torch.from_numpy(oracle.neg_cent_autocast_np(z.cpu().numpy(), m.float().cpu().numpy(), ls.float().cpu().numpy(),
+                                                        str(dtype).split(".")[1], stats_lowp=True)).cuda()
+    scale = want.abs().max()
+    for a, b_ in ((got, want), (got, rest), (rest, want)):
+        assert ((a - b_).abs() <= 2e-6 * scale).float().mean().item() >= 0.9
+    # without the flag (stats widened by the caller beforehand) term 1 differs visibly
+    plain = vits_b200.neg_cent(z, m.float(), ls.float(), autocast_dtype=dtype)
+    assert ((plain - want).abs() <= 2e-6 * scale).float().mean().item() < 0.9
+
+
 def test_neg_cent_autocast_mode_rejects_other_types():
     import vits_b200
     z, m, ls = _inputs(1, 192, 64, 32, seed=1)

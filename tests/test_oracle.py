@@ -122,3 +122,33 @@ def test_oracle_vs_real_model_capture(oracle, synth_golden):
     np.testing.assert_array_equal(path_to_index(path.numpy()), s["index"])
     np.testing.assert_array_equal(mask.squeeze(1).sum(1)[:, 0].numpy().astype(np.int32), s["y_lengths"])
     np.testing.assert_array_equal(mask.squeeze(1).sum(2)[:, 0].numpy().astype(np.int32), s["x_lengths"])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_neg_cent_autocast_restatement_vs_torch_cpu_autocast(oracle, dtype):
+    """the numpy restatement of SynthesizerTrn.py:223-232 as it evaluates
+    under autocast, against the literal expression inside torch's CPU autocast (fp32 inputs: only the einsums
+    change precision).  torch accumulates the products in fp32 in its own order, the restatement rounds the
+    exact sum once, so a few einsum outputs may fall on the other side of a rounding boundary."""
+    import math
+    g = torch.Generator().manual_seed(3)
+    B, C, T_y, T_x = 2, 192, 70, 33
+    z = torch.randn(B, C, T_y, generator=g)
+    m = torch.randn(B, C, T_x, generator=g)
+    ls = torch.randn(B, C, T_x, generator=g) * 0.3
+    with torch.no_grad(), torch.autocast("cpu", dtype=dtype):
+        iv = torch.exp(-2 * ls)
+        e2 = torch.einsum("bdt, bds -> bts", -0.5 * (z ** 2), iv)
+        e3 = torch.einsum("bdt, bds -> bts", z, m * iv)
+        want = (torch.sum(-0.5 * math.log(2 * math.pi) - ls, [1], keepdim=True) + e2 + e3
+                + torch.sum(-0.5 * (m ** 2) * iv, [1], keepdim=True))
+    assert e2.dtype == dtype and e3.dtype == dtype and want.dtype == torch.float32
+    got = oracle.neg_cent_autocast_np(z.numpy(), m.numpy(), ls.numpy(), str(dtype).split(".")[1])
+    want = want.numpy()
+    scale = np.abs(want).max()
+    d = np.abs(got - want)
+    eps = torch.finfo(dtype).eps
+    assert d.max() <= eps * (e2.float().abs().max().item() + e3.float().abs().max().item()) + 1e-5 * scale
+    assert (d <= 2e-6 * scale).mean() >= 0.99
+    fp32 = oracle.neg_cent_torch(z, m, ls).numpy()              # and the mode is not the fp32 formulation
+    assert (np.abs(fp32 - want) <= 2e-6 * scale).mean() < 0.5

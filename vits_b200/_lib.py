@@ -64,7 +64,7 @@ def lib() -> ctypes.CDLL:
     L.mas_set_tuning.restype = None
     L.mas_set_tuning.argtypes = [c_int, c_int, c_int, c_int]
     L.mas_neg_cent_autocast.restype = c_int
-    L.mas_neg_cent_autocast.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]
+    L.mas_neg_cent_autocast.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]
     L.mas_set_neg_cent_impl.restype = None
     L.mas_set_neg_cent_impl.argtypes = [c_int]
     L.mas_set_debug_kernels.restype = None

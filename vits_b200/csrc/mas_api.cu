@@ -237,9 +237,10 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                        static_cast<cudaStream_t>(stream));
 }
 
-int mas_neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent, int gemm_dtype, int B,
-                          int C, int T_y, int T_x, mas_stream_t stream) {
-  return mas::neg_cent_autocast(z_p, m_p, logs_p, neg_cent, gemm_dtype, B, C, T_y, T_x, static_cast<cudaStream_t>(stream));
+int mas_neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent, int gemm_dtype,
+                          int stats_lowp, int B, int C, int T_y, int T_x, mas_stream_t stream) {
+  return mas::neg_cent_autocast(z_p, m_p, logs_p, neg_cent, gemm_dtype, stats_lowp, B, C, T_y, T_x,
+                                static_cast<cudaStream_t>(stream));
 }
 
 int mas_path_durations(const int32_t* index, float* w, int B, int T_y, int T_x, mas_stream_t stream) {

@@ -35,8 +35,8 @@ int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out
              int B, int C, int T_y, int T_x, cudaStream_t st);
 size_t neg_cent_scratch_bytes(int B, int C, int T_y, int T_x);
 void set_neg_cent_impl(int impl);
-int neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* out, int gemm_dtype, int B, int C,
-                      int T_y, int T_x, cudaStream_t st);
+int neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* out, int gemm_dtype, int stats_lowp,
+                      int B, int C, int T_y, int T_x, cudaStream_t st);
 
 // mas_neg_cent_tc.cu
 int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,

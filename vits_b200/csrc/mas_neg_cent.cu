@@ -44,7 +44,7 @@ __device__ __forceinline__ float rnd(float x) {
 template <int RND>
 __global__ void __launch_bounds__(256) neg_cent_simt_kernel(const float* __restrict__ z_p, const float* __restrict__ m_p,
                                                             const float* __restrict__ logs_p, float* __restrict__ out,
-                                                            int C, int T_y, int T_x) {
+                                                            int C, int T_y, int T_x, int stats_lowp) {
   __shared__ float sA2[TK][TM];   // -0.5 z^2
   __shared__ float sZ[TK][TM];    // z
   __shared__ float sIv[TK][TN];   // exp(-2 logs)
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(256) neg_cent_simt_kernel(const float* __restr
             if constexpr (RND == 0) {
               bias += (-kHalfLog2Pi - l) + (-0.5f * (m * m)) * sIv[d][tid];
             } else {
-              bias += -kHalfLog2Pi - l;
+              // :225 is plain arithmetic, so it runs in the dtype of logs_p: TextEncoder.proj returns the
+              // low-precision type under autocast (TextEncoder.py:101-104) and each element is rounded to it
+              // before sum() -- on autocast's fp32 list -- adds them up in fp32
+              bias += stats_lowp ? rnd<RND>(-kHalfLog2Pi - l) : -kHalfLog2Pi - l;
               bias4 += (-0.5f * (m * m)) * expf(-2.0f * l);  // fp32 inverse variance, not the rounded operand
             }
           }
@@ -181,22 +184,22 @@ int neg_cent(const float* z_p, const float* m_p, const float* logs_p, float* out
   if (g_impl != 0) return neg_cent_tc(z_p, m_p, logs_p, out, scratch, scratch_bytes, B, C, T_y, T_x, st);
   dim3 grid((T_x + TN - 1) / TN, (T_y + TM - 1) / TM, B);
   if (grid.y > 65535) return MAS_E_BAD_SHAPE;
-  neg_cent_simt_kernel<0><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x);
+  neg_cent_simt_kernel<0><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x, 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return MAS_OK;
 }
 
-int neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* out, int gemm_dtype, int B, int C,
-                      int T_y, int T_x, cudaStream_t st) {
+int neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* out, int gemm_dtype, int stats_lowp,
+                      int B, int C, int T_y, int T_x, cudaStream_t st) {
   if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0 || B > 65535) return MAS_E_BAD_SHAPE;
   if (!z_p || !m_p || !logs_p || !out) return MAS_E_NULL;
   if (gemm_dtype != MAS_F16 && gemm_dtype != MAS_BF16) return MAS_E_BAD_DTYPE;
   dim3 grid((T_x + TN - 1) / TN, (T_y + TM - 1) / TM, B);
   if (grid.y > 65535) return MAS_E_BAD_SHAPE;
-  if (gemm_dtype == MAS_F16) neg_cent_simt_kernel<1><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x);
-  else neg_cent_simt_kernel<2><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x);
+  if (gemm_dtype == MAS_F16) neg_cent_simt_kernel<1><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x, stats_lowp);
+  else neg_cent_simt_kernel<2><<<grid, 256, 0, st>>>(z_p, m_p, logs_p, out, C, T_y, T_x, stats_lowp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();

@@ -30,8 +30,10 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor, *,
 
     ``autocast_dtype=torch.float16`` (or ``bfloat16``) selects the autocast-parity mode instead: the numerics
     the reference has as trained under ``autocast(fp16_run)`` (train_and_evaluate.py:55) -- both einsums on
-    operands rounded to that type with their outputs rounded to it, everything else fp32.  It runs on CUDA
-    cores and is there to reproduce as-trained alignments, not for speed."""
+    operands rounded to that type with their outputs rounded to it, everything else fp32 -- except that when
+    ``logs_p`` itself arrives in that type (TextEncoder.proj's output under autocast) the elementwise part of
+    :225 is rounded to it too, as plain tensor arithmetic in that dtype is.  It runs on CUDA cores and is there
+    to reproduce as-trained alignments, not for speed."""
     if not (z_p.is_cuda and m_p.is_cuda and logs_p.is_cuda):
         raise ValueError("neg_cent needs CUDA tensors (there is no CPU implementation)")
     if z_p.dim() != 3 or m_p.dim() != 3 or m_p.shape != logs_p.shape or z_p.shape[:2] != m_p.shape[:2]:
@@ -48,7 +50,9 @@ def neg_cent(z_p: torch.Tensor, m_p: torch.Tensor, logs_p: torch.Tensor, *,
             code = {torch.float16: 1, torch.bfloat16: 2}.get(autocast_dtype)
             if code is None:
                 raise ValueError("autocast_dtype must be torch.float16 or torch.bfloat16")
-            rc = L.mas_neg_cent_autocast(z.data_ptr(), m.data_ptr(), ls.data_ptr(), out.data_ptr(), code, B, C, T_y, T_x, stream)
+            stats_lowp = int(logs_p.dtype == autocast_dtype)   # :225 ran in logs_p's own dtype
+            rc = L.mas_neg_cent_autocast(z.data_ptr(), m.data_ptr(), ls.data_ptr(), out.data_ptr(), code, stats_lowp,
+                                         B, C, T_y, T_x, stream)
             _lib.check(rc, "mas_neg_cent_autocast")
             return out
         nbytes = int(L.mas_neg_cent_scratch_bytes(B, C, T_y, T_x))
