@@ -70,10 +70,17 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def busy_until(self, work, rows, timeout_s):
+        """Run `work()` (enqueue + synchronize) over and over until `rows` samples have arrived."""
+        import torch
+        t0 = time.time()
+        while self.proc is not None and len(self.rows) < rows and time.time() - t0 < timeout_s:
+            work()
+            torch.cuda.synchronize()
+
     def stop(self):
         if self.proc is None:
             return None
-        time.sleep(0.15)
         self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
@@ -335,20 +342,29 @@ def run_ours(args, rank, world, local_rank):
             for i in range(n % nbuf):
                 graphs[i].replay()
 
-        run_steps(warmup)
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        barrier()
+        # nvidia-smi needs a good fraction of a second to start (longer with several ranks starting one at once),
+        # the K timed steps may last only milliseconds: rank 0 starts it first and keeps the GPU busy with the
+        # same steps, untimed, until the first sample is in and again after the timed region until one more is,
+        # so the samples bracket the timed region under its own load.
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()
+        run_steps(warmup)
+        if sampler:
+            sampler.busy_until(lambda: run_steps(nbuf), len(sampler.rows) + 1, 6.0)
+        barrier()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run_steps(steps)
         e1.record()
+        n1 = _lib.launch_count()
+        if sampler:
+            sampler.busy_until(lambda: run_steps(nbuf), len(sampler.rows) + 1, 1.5)
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
-        launches = (_lib.launch_count() - n0) if graphs is None else launches_per_step * steps
+        launches = (n1 - n0) if graphs is None else launches_per_step * steps
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -408,6 +424,36 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         # the link itself, for scale: one plain pinned copy of a whole [B,T_y,T_x] plane each way
         link = None
+        all_ranks_duplex = None
+        if world > 1:
+            # every rank's link busy in both directions at once: what the HOST (root complexes, memory) sustains
+            # when all the ranks copy together -- the bound of this leg beyond a few GPUs per host
+            da, db = (torch.empty(B, T_y, T_x, dtype=torch.float32, device=dev) for _ in range(2))
+            sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def both_all(n):
+                for _ in range(n):
+                    with torch.cuda.stream(sa):
+                        da.copy_(h_vals[0], non_blocking=True)
+                    with torch.cuda.stream(sb):
+                        h_vals[1].copy_(db, non_blocking=True)
+                torch.cuda.synchronize()
+            both_all(1)
+            barrier()
+            t1 = time.perf_counter()
+            both_all(5)
+            tl = torch.tensor([time.perf_counter() - t1], device=dev, dtype=torch.float64)
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            per_plane_s = float(tl.item()) / 5
+            all_ranks_duplex = {"aggregate_gbs": world * 2 * plane_bytes / per_plane_s / 1e9,
+                                "bound": world * B / (per_plane_s * valid_row_bytes / plane_bytes),
+                                "note": "all ranks copying one plane each way at the same time (pinned, max over ranks); "
+                                        "bound = whole-job alignments/s if a step cost exactly those copies"}
+            h_vals[1].copy_(ncs[1 % len(ncs)])
+            del da, db
+        tmin = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         if rank == 0:
             d_tmp = torch.empty(B, T_y, T_x, dtype=torch.float32, device=dev)
             gbs = []
@@ -447,7 +493,8 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": valid_row_bytes + 8 * B, "d2h_bytes_per_step": valid_row_bytes + 64,
                "copied": "leading rows of every utterance up to the longest of its group, both directions (the "
                          "padded tail is never needed, as in core.pyx:13-33); host paths buffer zero-filled once",
-               "pcie_link": link,
+               "pcie_link": link, "pcie_all_ranks_duplex": all_ranks_duplex,
+               "rank_seconds": {"min": float(tmin.item()), "max": float(td.item())},
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",
                "api": "mas_maximum_path_c_host (twin of core.pyx:38), pinned host buffers"}
         L.mas_host_release()
