@@ -777,7 +777,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     dp.mask = mask; dp.mask_dtype = mask_dtype; dp.msb = msb; dp.msy = msy; dp.msx = msx;
     dp.lens = lens; dp.status = status; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
     dp.wo_counters = status + 4;
-    dp.pdl = g_tune_pdl;
+    dp.pdl = g_tune_pdl == 2;  // see set_tuning: the forward kernel is an ordinary launch by default
     dp.B = B; dp.T_y = T_y; dp.T_x = T_x;
     dp.S = dc.S; dp.W = dc.W; dp.TXP = TXP; dp.G = L.G; dp.BR = dc.BR;
     dp.sm = dc.sm;
@@ -795,7 +795,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
     fp.lenstag = stream ? lenstag : nullptr;
     fp.wo_counters = status + 4;
-    fp.pdl = g_tune_pdl;
+    fp.pdl = g_tune_pdl == 2;
     fp.trace = g_trace;
     fp.B = B; fp.T_y = T_y; fp.T_x = T_x;
     fp.S = fc.S; fp.W = fc.W; fp.H = fc.H; fp.TXP = TXP; fp.G = L.G; fp.BR = fc.BR;
@@ -910,6 +910,12 @@ void set_debug_kernels(int mask) { g_debug_kernels = mask; }
 void set_timeline(unsigned long long* dev_ptr) { g_timeline = dev_ptr; }
 void set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
+// pdl: 0 = every kernel an ordinary launch; 1 (default) = write-out and backtrack kernels launched
+// programmatically behind the forward kernel of their call, the forward kernel itself ordinarily; 2 = the
+// forward kernel programmatically too, behind whatever precedes it in the stream.  2 was the default until it
+// was measured call by call (tools/timeline_gap.py, four calls in one graph, c2 full-length): the next call's
+// forward CTAs then become resident one by one as SMs drain during the current call, and the DP of every call
+// but the first takes 40-44 us instead of 33 us -- far more than the ~1.3 us of launch latency the edge hides.
 void set_tuning(int K, int R, int S, int pdl) {
   g_tune_K = K;
   g_tune_R = R;
