@@ -342,8 +342,25 @@ def run_ours(args, rank, world, local_rank):
             per = nbuf * passes
             for _ in range(n // per):
                 multi.replay()
-            for i in range(n % per):
-                graphs[i % nbuf].replay()
+            if n % per:
+                tail_graph(n % per).replay()
+
+        tails = {}
+
+        def tail_graph(k):
+            """k < steps_per_graph consecutive steps as one graph (captured once, before the timed region)."""
+            if k not in tails:
+                gk = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gk):
+                    for i in range(k):
+                        step(i)
+                tails[k] = gk
+            return tails[k]
+
+        if graphs is not None:
+            for n in (warmup, steps, nbuf):
+                if n % (nbuf * passes):
+                    tail_graph(n % (nbuf * passes))
 
         # nvidia-smi needs a good fraction of a second to start (longer with several ranks starting one at once),
         # the K timed steps may last only milliseconds: rank 0 starts it first and keeps the GPU busy with the

@@ -83,7 +83,7 @@ def test_every_kernel_configuration(mp, oracle, K, R):
         t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
         want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
         for stages, pdl, fused, helpers in ((2, 1, 0, 0), (5, 0, 0, 0), (3, 1, 1, 1), (4, 0, 1, 4), (0, 1, -1, 0),
-                                            (3, 1, 2, 0), (0, 0, 2, 0), (0, 1, 3, 0)):
+                                            (3, 1, 2, 0), (0, 0, 2, 0), (0, 1, 3, 0), (0, 2, -1, 0), (3, 2, 1, 1)):
             L.mas_set_tuning(K, R, stages, pdl)
             L.mas_set_tuning2(fused, helpers)
             got = _gpu_path(mp, nc, t_ys, t_xs)
@@ -106,7 +106,7 @@ def test_wavefront_forward_kernel_configurations(mp, oracle, K, ring_mode):
             nc = (rng.standard_normal(shape) * 2 - 1).astype(np.float32)
             t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
             want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
-            for slots, pdl in ((smin, 1), (0, 0), (0, 1)):
+            for slots, pdl in ((smin, 1), (0, 0), (0, 1), (0, 2)):   # pdl 2: forward kernel launched programmatically too
                 L.mas_set_tuning(0, 0, 0, pdl)
                 L.mas_set_tuning2(3, 0)
                 L.mas_set_tuning3(-1, ring_mode, slots, K)
