@@ -615,7 +615,12 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg) {
   int linear = 1, skew = 0;
   if (g_tune_ring >= 1 && g_tune_ring <= 3) skew = g_tune_ring;
   else if (g_tune_ring == 4) { linear = 0; skew = 1; }
-  else if (nphys >= 4) skew = 1;       // measured at c2: 25.3 us with skew 1 or 2, 29.8 us with skew 3 (more lag per hop)
+  // Measured back to back (tools/sweep_wf.py --ab, one graph of 8 calls, alternating): three DP warps (c2,
+  // T_x = 192) 39.7 / 38.1 / 44.2 us per call at skew 1 / 2 / 3 with variable lengths (40.3 / 39.7 / 46.3
+  // full-length); four DP warps (c3, T_x = 256) 53.8 / 55.2 / 69.7 us.  A larger skew takes more of the
+  // neighbour's SHFL latency off the chain but adds a superstep of lag per warp hop.
+  else if (nphys >= 5 && W <= 3) skew = 2;
+  else if (nphys >= 4) skew = 1;
   else { linear = 0; skew = 1; }
   const int Q = (31 * skew + 31) / 32;
   const int smin = linear ? Q + 2 : 3;
