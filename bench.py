@@ -213,6 +213,9 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
     return kind, res, {"cpu_model": cpu_model, "cpu_count": os.cpu_count(), "affinity": threads}
 
 
+print_line = lambda line: print(json.dumps(line), flush=True)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -251,7 +254,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(line)
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -582,7 +585,7 @@ def run_ours(args, rank, world, local_rank):
                                     "sample": f"{res['wrapper']['reps']} full batches of the same workload "
                                               "(reference wrapper marshalling + compiled core.pyx, as shipped: serial)",
                                     "variants": res, "host": host}
-        print(json.dumps(line))
+        print_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -689,6 +692,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL announces its version on
+    # stdout when NCCL_DEBUG is set) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_line
+    print_line = lambda line: print(json.dumps(line), file=json_out, flush=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
