@@ -152,3 +152,15 @@ def test_neg_cent_autocast_restatement_vs_torch_cpu_autocast(oracle, dtype):
     assert (d <= 2e-6 * scale).mean() >= 0.99
     fp32 = oracle.neg_cent_torch(z, m, ls).numpy()              # and the mode is not the fp32 formulation
     assert (np.abs(fp32 - want) <= 2e-6 * scale).mean() < 0.5
+
+
+def test_low_precision_rounding_helper_matches_torch(oracle):
+    """oracle._round_to (nearest-even fp32 -> fp16 / bf16 -> fp32) against torch's casts, ties and subnormals included."""
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.standard_normal(20000).astype(np.float32) * 300,
+                        rng.standard_normal(2000).astype(np.float32) * 1e-6,
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11,
+                                  65504.0, -65504.0, 6e-8, 3e-8], dtype=np.float32)])
+    t = torch.from_numpy(a)
+    np.testing.assert_array_equal(oracle._round_to(a, "bfloat16"), t.to(torch.bfloat16).float().numpy())
+    np.testing.assert_array_equal(oracle._round_to(a, "float16"), t.to(torch.float16).float().numpy())
