@@ -122,6 +122,15 @@ def host_entry_groups(B, plane_bytes):
     return out
 
 
+def workload_string(name, B, T_y, T_x, ragged, scaling="weak"):
+    """`config.workload`, word for word the same in both arms (the driver compares the strings)."""
+    per = "/GPU" if scaling == "weak" else " global, split over the GPUs"
+    lens = ("variable lengths (SURVEY 8d: t_x~U[T_x/2,T_x], t_y~U[max(t_x,T_y/2),T_y], element 0 full)" if ragged
+            else "full-length")
+    return (f"{name}: B={B}{per} T_y<={T_y} T_x<={T_x} {lens} with [B,T_y,T_x] fp32 mask, "
+            f"neg_cent~N(-400,20^2) fp32 -> fp32 path")
+
+
 def make_lengths(rng, B, T_y, T_x, ragged):
     if not ragged:
         return np.full(B, T_y, np.int32), np.full(B, T_x, np.int32)
@@ -161,7 +170,8 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
         return float(np.median(ts)), float(min(ts)), len(ts)
 
     res = {}
-    med, best, n = timeit(lambda: mas_oracle.maximum_path(nc, mask, core=core), budget_s * 0.5)
+    ref_fn, _, _ = reference_maximum_path()
+    med, best, n = timeit(lambda: ref_fn(nc, mask), budget_s * 0.5)
     res["wrapper"] = {"median_s": med, "min_s": best, "reps": n, "alignments_per_s": B / med}
     values = nc.numpy().astype(np.float32)
     ty32, tx32 = np.asarray(t_ys, np.int32), np.asarray(t_xs, np.int32)
@@ -190,7 +200,7 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
             nc_d, mask_d = nc.cuda(), mask.cuda()
 
             def wrapped_cuda():
-                out = mas_oracle.maximum_path(nc_d, mask_d, core=core)
+                out = ref_fn(nc_d, mask_d)
                 torch.cuda.synchronize()
                 return out
             med, best, n = timeit(wrapped_cuda, budget_s * 0.15)
@@ -216,41 +226,95 @@ def cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=10.0, seed=1234):
 print_line = lambda line: print(json.dumps(line), flush=True)
 
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    B, T_y, T_x = WORKLOADS[args.workload]
-    rng = np.random.default_rng(1234)
-    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, not args.full_length)
-    import torch
+def reference_maximum_path():
+    """The reference's own `monotonic_align.maximum_path` (its unmodified __init__.py over its own compiled core.pyx,
+    installed into the git-ignored baseline/_ref/vits by tools/install_reference.py); when that tree is absent, the
+    oracle's restatement of the same wrapper around the compiled core (or around the C port)."""
+    pkg = os.path.join(ROOT, "baseline", "_ref", "vits", "monotonic_align")
+    if os.path.exists(os.path.join(pkg, "__init__.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_monotonic_align_stock", os.path.join(pkg, "__init__.py"),
+                                                      submodule_search_locations=[pkg])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["ref_monotonic_align_stock"] = mod
+        try:
+            spec.loader.exec_module(mod)
+            return mod.maximum_path, "reference", "baseline/_ref/vits/monotonic_align: the reference's unmodified __init__.py:7-20 + its core.pyx built with its setup.py's flags (no OpenMP => serial prange)"
+        except Exception:
+            pass
     from oracle import mas_oracle
     stock = mas_oracle.load_ref_core("stock")
     core = stock if stock is not None else mas_oracle.maximum_path_c
-    kind = "reference" if stock is not None else "port"
-    g = torch.Generator().manual_seed(1234)
+    return (lambda nc, mask: mas_oracle.maximum_path(nc, mask, core=core)), ("reference" if stock is not None else "port"), \
+        "oracle.mas_oracle.maximum_path (restatement of __init__.py:7-20) around " + ("the reference's compiled core.pyx" if stock is not None else "the C port")
+
+
+def reference_worker(job):
+    """One CPU process of the reference arm: what one rank of the reference's mp.spawn (train.py:46) pays per step."""
+    workload, full_length, steps, warm, threads, shard, nshards, strong = job
+    import torch
+    torch.set_num_threads(max(1, threads))           # BEFORE the timed loop (torchrun exports OMP_NUM_THREADS=1)
+    B, T_y, T_x = WORKLOADS[workload]
+    if strong:
+        B = max(1, B // nshards)
+    rng = np.random.default_rng(1234 + shard)
+    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, not full_length)
+    fn, kind, path = reference_maximum_path()
+    from oracle import mas_oracle
+    g = torch.Generator().manual_seed(1234 + shard)
     nc = torch.randn(B, T_y, T_x, generator=g) * 20 - 400
     mask = mas_oracle.attn_mask(torch.as_tensor(t_xs), torch.as_tensor(t_ys), T_x, T_y, torch.float32)
-    steps = min(args.steps, 50)
-    warm = min(args.warmup, 5)
     for _ in range(max(warm, 1)):
-        mas_oracle.maximum_path(nc, mask, core=core)
+        fn(nc, mask)
     t0 = time.perf_counter()
     for _ in range(steps):
-        mas_oracle.maximum_path(nc, mask, core=core)
-    dt = time.perf_counter() - t0
-    value = B * steps / dt
-    _, extra, host = cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=6.0)
+        fn(nc, mask)
+    return time.perf_counter() - t0, B, kind, path, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores.  Rank 0 alone runs
+    and prints; with --gpus N > 1 it runs N worker processes side by side, one per would-be rank, each on its own shard
+    and with its share of the host threads -- the reference under its own mp.spawn (train.py:46) runs one CPU alignment
+    per rank -- and reports N x B / (slowest worker's time), so the whole-job figures of the two arms compare."""
+    if rank != 0:
+        return
+    n = max(1, args.gpus)
+    strong = args.scaling == "strong"
+    B, T_y, T_x = WORKLOADS[args.workload]
+    steps = min(args.steps, 50)
+    warm = min(args.warmup, 5)
+    threads_all = len(os.sched_getaffinity(0))
+    threads = max(1, threads_all // n)
+    jobs = [(args.workload, args.full_length, steps, warm, threads, i, n, strong) for i in range(n)]
+    if n == 1:
+        results = [reference_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        with mp.get_context("spawn").Pool(n) as pool:
+            results = pool.map(reference_worker, jobs)
+    dt = max(r[0] for r in results)
+    total_B = sum(r[1] for r in results)
+    kind, path = results[0][2], results[0][3]
+    value = total_B * steps / dt
+    import torch
+    rng = np.random.default_rng(1234)
+    t_ys, t_xs = make_lengths(rng, results[0][1], T_y, T_x, not args.full_length)
+    extra = host = None
+    if n == 1:
+        _, extra, host = cpu_reference_timing(results[0][1], T_y, T_x, t_ys, t_xs, budget_s=6.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: B={B} T_y<={T_y} T_x<={T_x} {'full-length' if args.full_length else 'variable lengths'} "
-                               "neg_cent~N(-400,20^2), CPU tensors in and out",
-                   "path": "monotonic_align.maximum_path wrapper marshalling (__init__.py:14-20) + the reference's "
-                           "compiled core.pyx, built with its setup.py's flags (no OpenMP => serial prange)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
-                         "torch_threads": torch.get_num_threads(),
-                         "sample": f"{steps} full batches of the workload", "variants": extra, "host": host},
+        "config": {"workload": workload_string(args.workload, B, T_y, T_x, not args.full_length, args.scaling),
+                   "arm": "CPU tensors in and out; " + path,
+                   "processes": n, "torch_threads_per_process": results[0][4],
+                   "worker_seconds": [r[0] for r in results]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n, "kind": kind,
+                         "torch_threads": results[0][4] * n,
+                         "sample": f"{steps} full batches of the workload in each of {n} process(es)", "variants": extra, "host": host},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,7 +335,11 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    B, T_y, T_x = WORKLOADS[args.workload]
+    B_cfg, T_y, T_x = WORKLOADS[args.workload]
+    strong = args.scaling == "strong"
+    # weak: B utterances per GPU (batch_size is per replica in the reference's DDP, train.py:101); strong: the
+    # configuration's batch is the GLOBAL batch, split over the ranks (c3, 32 -> 4 per GPU on 8 GPUs)
+    B = max(1, B_cfg // world) if strong else B_cfg
 
     # rotating buffer sets so that consecutive steps never find their input or output in L2
     plane_bytes = B * T_y * T_x * 4
@@ -364,6 +432,13 @@ def run_ours(args, rank, world, local_rank):
             for n in (warmup, steps, nbuf):
                 if n % (nbuf * passes):
                     tail_graph(n % (nbuf * passes))
+            # every graph object the timed region replays has been replayed at least once before it (the first
+            # replay of a graph pays its upload; r1's driver run timed exactly that: 46 instead of 40 us per step)
+            if steps // (nbuf * passes):
+                multi.replay()
+            if steps % (nbuf * passes):
+                tail_graph(steps % (nbuf * passes)).replay()
+            torch.cuda.synchronize()
 
         # nvidia-smi needs a good fraction of a second to start (longer with several ranks starting one at once),
         # the K timed steps may last only milliseconds: rank 0 starts it first and keeps the GPU busy with the
@@ -520,7 +595,34 @@ def run_ours(args, rank, world, local_rank):
                "rank_seconds": {"min": float(tmin.item()), "max": float(td.item())},
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",
                "api": "mas_maximum_path_c_host (twin of core.pyx:38), pinned host buffers"}
+        # the same leg through the repo's own PYTHON API, exactly as a user of the reference would call it with CPU
+        # tensors: ordinary (pageable) torch tensors in, a new fp32 tensor out, mask given as the dense tensor
+        py_steps = max(3, min(args.steps, 10))
+        nc_cpu = [hv.clone() for hv in h_vals]          # pageable copies
+        mask_cpu = mask.cpu()
+        for i in range(2):
+            out_cpu = vits_b200.maximum_path(nc_cpu[i % 2], mask_cpu)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(py_steps):
+            out_cpu = vits_b200.maximum_path(nc_cpu[i % 2], mask_cpu)
+        dtp = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtp, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert out_cpu.dtype == torch.float32 and np.array_equal(
+                out_cpu.numpy().astype(np.int32), mas_oracle.maximum_path_numpy(nc_cpu[(py_steps - 1) % 2].numpy(), t_ys, t_xs))
+        e2e["python_api"] = {"value": world * B * py_steps / float(dtp.item()), "unit": UNIT, "steps": py_steps,
+                             "api": "vits_b200.maximum_path(neg_cent_cpu, mask_cpu): pageable CPU tensors in, new fp32 CPU "
+                                    "tensor out (lengths from the mask on the host, mas_maximum_path_host inside)"}
+        del nc_cpu, mask_cpu, out_cpu
         L.mas_host_release()
+
+    # --- c3 strong scaling (BASELINE.json configs[2]: B = 32 global, batch-sharded over the GPUs), reported as an
+    # extra key of every N > 1 line; `--scaling strong --workload c3` makes it the headline instead ---
+    c3_strong = None
+    if world > 1 and not (strong and args.workload == "c3"):
+        c3_strong = strong_scaling_probe("c3", world, rank, dev, barrier)
 
     # --- multi-GPU verification (outside the timed region): all-gather the per-frame indices over NCCL ---
     verified = None
@@ -560,17 +662,17 @@ def run_ours(args, rank, world, local_rank):
                             "decision words (and 3.1 MB of tag clears), mas_writeout 50.3 MB written")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: B={B}/GPU T_y<={T_y} T_x<={T_x} "
-                                   f"{'variable lengths (SURVEY 8d: t_x~U[T_x/2,T_x], t_y~U[max(t_x,T_y/2),T_y], element 0 full)' if primary_ragged else 'full-length'}"
-                                   f" with [B,T_y,T_x] fp32 mask, neg_cent~N(-400,20^2) fp32 -> fp32 path",
+            "config": {"workload": workload_string(args.workload, B_cfg, T_y, T_x, primary_ragged, args.scaling),
+                       "arm": f"device-resident tensors, {B} utterances on each of {world} GPU(s)",
                        "other_variant": other,
                        "l2": f"inputs larger than L2: {nbuf} rotating (neg_cent, path) buffer sets = "
                              f"{2 * nbuf * plane_bytes / 1e6:.0f} MB, no flush kernel in the timed region",
                        "launch": (f"CUDA graph replay, {R['steps_per_graph']} consecutive steps per graph cycling over the {nbuf} rotating buffer sets" if graphs is not None else "eager ctypes launches"),
                        "parity_checked": parity, "multi_gpu_verified": verified},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "path_breakdown": breakdown,
+            "c3_strong": c3_strong,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes,
@@ -581,6 +683,16 @@ def run_ours(args, rank, world, local_rank):
         }
         if not args.no_cpu and world == 1:
             kind, res, host = cpu_reference_timing(B, T_y, T_x, t_ys, t_xs, budget_s=args.cpu_budget)
+            if e2e is not None:   # what the host-buffer leg is compared with, level by level
+                e2e["vs_cpu"] = {
+                    "c_entry_vs_reference_wrapper": e2e["value"] / res["wrapper"]["alignments_per_s"],
+                    "c_entry_vs_reference_core_only": e2e["value"] / res["core_only"]["alignments_per_s"],
+                    "c_entry_vs_openmp_steelman_core_only": (e2e["value"] / res["omp_steelman_core_only"]["alignments_per_s"]
+                                                             if "omp_steelman_core_only" in res else None),
+                    "python_api_vs_reference_wrapper": e2e["python_api"]["value"] / res["wrapper"]["alignments_per_s"],
+                    "note": "same-level pairs: C entry <-> core_only (core.pyx:38 on prepared arrays); Python API <-> wrapper "
+                            "(__init__.py:7-20 on CPU tensors).  The OpenMP steelman is the reference's core rebuilt with "
+                            "-fopenmp on every host thread; this leg is PCIe-bound (pcie_link.duplex_bound)"}
             line["cpu_baseline"] = {"value": res["wrapper"]["alignments_per_s"], "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": f"{res['wrapper']['reps']} full batches of the same workload "
                                               "(reference wrapper marshalling + compiled core.pyx, as shipped: serial)",
@@ -588,6 +700,49 @@ def run_ours(args, rank, world, local_rank):
         print_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling_probe(workload, world, rank, dev, barrier, steps=40):
+    """The workload's batch as a GLOBAL batch split over the ranks (c3, 32 -> 4 per GPU on 8 GPUs):
+    every rank aligns B/world utterances; whole-job alignments/s = B / (slowest rank's time per step)."""
+    import torch
+    import torch.distributed as dist
+    import vits_b200
+    Bg, T_y, T_x = WORKLOADS[workload]
+    B = max(1, Bg // world)
+    rng = np.random.default_rng(4321 + rank)
+    t_ys, t_xs = make_lengths(rng, B, T_y, T_x, True)
+    ty_d, tx_d = torch.as_tensor(t_ys, device=dev), torch.as_tensor(t_xs, device=dev)
+    ym = torch.arange(T_y, device=dev)[None, :] < ty_d[:, None]
+    xm = torch.arange(T_x, device=dev)[None, :] < tx_d[:, None]
+    mask = (ym[:, :, None] & xm[:, None, :]).float()
+    nbuf = 8
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    ncs = [torch.randn(B, T_y, T_x, generator=g, device=dev) * 20 - 400 for _ in range(nbuf)]
+    outs = [None] * nbuf
+
+    def step(i):
+        outs[i % nbuf] = vits_b200.maximum_path(ncs[i % nbuf], mask)
+    for i in range(nbuf):
+        step(i)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(steps):
+            step(i)
+    gr.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gr.replay()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"workload": workload_string(workload, Bg, T_y, T_x, True, "strong"), "scaling": "strong", "n_gpus": world,
+            "utterances_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "note": "device-resident inputs, one CUDA graph of all steps over 8 rotating buffers, max over ranks"}
 
 
 def contraction_and_e2e(B, T_y, T_x, t_ys, t_xs, dev, C=192, reps=5):
@@ -679,7 +834,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS) + ["c5"],
+                    help="c1-c4: the alignment path alone (SURVEY.md 8d shapes); c5: the reference's training step with "
+                         "the drop-in (bench_c5.py)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's B per GPU; strong: the workload's B is the global batch, split over the GPUs")
+    ap.add_argument("--c5-batch", type=int, default=32, help="utterances per GPU in the c5 training step")
     ap.add_argument("--full-length", action="store_true",
                     help="headline on the full-length variant (default: variable lengths, BASELINE.json configs[1])")
     ap.add_argument("--no-graph", action="store_true")
@@ -699,7 +859,10 @@ def main():
     os.dup2(2, 1)
     global print_line
     print_line = lambda line: print(json.dumps(line), file=json_out, flush=True)
-    if args.impl == "reference":
+    if args.workload == "c5":
+        import bench_c5
+        bench_c5.main(args, print_line)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

@@ -46,7 +46,8 @@ enum {
   MAS_STATUS_TX_GT_TY = 1,   /* some utterance had t_x > t_y                     */
   MAS_STATUS_EMPTY = 2,      /* some utterance had t_x < 1 or t_y < 1            */
   MAS_STATUS_TOO_LONG = 4,   /* some utterance had t_y > T_y or t_x > T_x        */
-  MAS_STATUS_TIMEOUT = 8     /* internal: a kernel gave up waiting for another   */
+  MAS_STATUS_TIMEOUT = 8     /* internal: a kernel gave up waiting (2 s) for an earlier kernel of the stream; the
+                              * utterance's path is all-zero / index -1, never built from incomplete data */
 };
 
 int mas_abi_version(void);
@@ -58,6 +59,12 @@ const char* mas_error_string(int code);
 size_t mas_maximum_path_scratch_bytes(int B, int T_y, int T_x);
 /* Byte offset of the int32 status word inside the scratch buffer. */
 size_t mas_scratch_status_offset(void);
+/* Host pointer to four int32 words (pinned, device-mapped, owned by the library, one set per device; the call
+ * returns the current device's): word k becomes 1 as soon as a kernel raises status bit k (1 << k).  Reading them
+ * costs nothing and needs no synchronisation -- the device word in the scratch needs a copy -- so a caller can
+ * poll for MAS_STATUS_TIMEOUT (results invalid: the affected utterances get an all-zero path and index -1) or the
+ * length errors between calls; it clears the words itself.  NULL when pinned memory is unavailable. */
+int32_t* mas_status_mirror(void);
 
 /*
  * mas_maximum_path -- replaces maximum_path_c (monotonic_align/core.pyx:36-42) together with the
@@ -100,7 +107,16 @@ int mas_maximum_path(const float* neg_cent,
  */
 int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs,
                             int B, int T_y, int T_x);
-/* Release the buffers cached by mas_maximum_path_c_host. */
+/*
+ * mas_maximum_path_host -- the same host-buffer entry for callers that want the path in their own element type
+ * (what the wrapper's final `.to(device=device, dtype=dtype)` produces, __init__.py:20) without a host-side cast
+ * pass: `paths` is a HOST buffer [B, T_y, T_x] of `path_dtype` (MAS_* code).  zero_tail != 0: the rows no copy
+ * writes are zeroed by the entry itself (memset overlapped with the copies), so `paths` may arrive uninitialised;
+ * zero_tail == 0: `paths` must arrive zero-filled, as for mas_maximum_path_c_host.
+ */
+int mas_maximum_path_host(void* paths, int path_dtype, int zero_tail, const float* values, const int32_t* t_ys,
+                          const int32_t* t_xs, int B, int T_y, int T_x);
+/* Release the buffers cached by the host-buffer entries (current device). */
 void mas_host_release(void);
 
 /*
@@ -171,7 +187,8 @@ uint64_t mas_launch_count(void);
 void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl);
 /* neg_cent implementation: -1 automatic, 0 fp32 CUDA cores, 1 tcgen05 (split-bf16). */
 void mas_set_neg_cent_impl(int impl);
-/* Benchmark isolation: bit0 forward DP, bit1 backtrack, bit2 write-out; default 7 (all). */
+/* Benchmark isolation: bit0 forward DP, bit1 backtrack, bit2 write-out; default 7 (all).  Test hook: 7|8 launches
+ * everything but the wavefront forward kernel, so the streaming backtrack runs into its watchdog (MAS_STATUS_TIMEOUT). */
 void mas_set_debug_kernels(int mask);
 /* fused: -1 automatic, 0 separate backtrack kernel after the forward kernel, 1 backtrack fused into the
  * forward kernel, 2 streaming backtrack kernel on the idle SMs while the forward kernel runs, 3 the same

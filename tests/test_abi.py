@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in _declared_functions():
         assert hasattr(L, name), f"libvits_mas.so does not export {name}"
-    assert L.mas_abi_version() == 1
+    assert L.mas_abi_version() == 2
     assert L.mas_scratch_status_offset() == 0
 
 

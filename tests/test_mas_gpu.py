@@ -336,3 +336,57 @@ def test_baseline_configs_full_size(mp, oracle, cfg, ragged):
     # idempotence / determinism: a second call gives the same bytes
     again = mp.maximum_path(nc, _mask(t_ys, t_xs, T_y, T_x, nc.device))
     assert torch.equal(out, again)
+
+
+def test_watchdog_timeout_is_loud_and_never_yields_a_garbage_path(oracle):
+    """A streaming-backtrack poll that gives up (here: the forward kernel is withheld through the test hook) must leave an
+    all-zero path / index -1, raise MAS_STATUS_TIMEOUT in the scratch word and in the host-mapped mirror, and make the NEXT
+    call fail loudly without any synchronisation -- never a path walked over words that did not arrive."""
+    import vits_b200
+    from vits_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    B, T_y, T_x = 2, 160, 40
+    nc = torch.from_numpy((rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)).cuda()
+    t_ys, t_xs = torch.tensor([160, 121]), torch.tensor([40, 33])
+    want = oracle.maximum_path_numpy(nc.cpu().numpy(), t_ys.numpy(), t_xs.numpy())
+    vits_b200.status_nosync(reset=True)
+    side = torch.cuda.Stream()                  # fresh stream = fresh, zeroed scratch: no stale tags to accept
+    L.mas_set_debug_kernels(7 | 8)
+    try:
+        with torch.cuda.stream(side):
+            path = vits_b200.maximum_path_from_lengths(nc, t_ys, t_xs)
+            side.synchronize()
+            assert int(path.abs().sum().item()) == 0
+            assert vits_b200.last_status(reset=True) & _lib.MAS_STATUS_TIMEOUT
+    finally:
+        L.mas_set_debug_kernels(7)
+    assert vits_b200.status_nosync() & _lib.MAS_STATUS_TIMEOUT
+    with pytest.raises(_lib.MasError):
+        vits_b200.maximum_path_from_lengths(nc, t_ys, t_xs)      # surfaced on the next call, mirror cleared
+    got = vits_b200.maximum_path_from_lengths(nc, t_ys, t_xs)
+    np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want)
+    assert vits_b200.status_nosync(reset=True) & _lib.MAS_STATUS_TIMEOUT == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(oracle):
+    """Per-device host state (shared-memory opt-ins, SM counts, host-entry buffers) -- ADVICE r1."""
+    import vits_b200
+    rng = np.random.default_rng(9)
+    B, T_y, T_x = 3, 700, 192
+    nc = (rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)
+    t_ys, t_xs = np.array([700, 650, 400], np.int32), np.array([192, 100, 150], np.int32)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs)
+    for d in (1, 0, 1):
+        dev = torch.device("cuda", d)
+        got = vits_b200.maximum_path_from_lengths(torch.from_numpy(nc).to(dev), torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+        assert got.device == dev
+        np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want)
+        z = torch.randn(2, 192, 300, device=dev)
+        m, ls = torch.randn(2, 192, 64, device=dev), torch.randn(2, 192, 64, device=dev) * 0.3
+        ref = oracle.neg_cent_torch(z, m, ls)
+        assert ((vits_b200.neg_cent(z, m, ls) - ref).abs().amax() / ref.abs().amax()).item() <= 1e-5
+        with torch.cuda.device(dev):
+            cpu = vits_b200.maximum_path_from_lengths(torch.from_numpy(nc), torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+        np.testing.assert_array_equal(cpu.numpy().astype(np.int32), want)

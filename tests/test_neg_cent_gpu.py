@@ -10,7 +10,7 @@ import math
 import pytest
 import torch
 
-from helpers import path_to_index, random_lengths
+from helpers import near_tie_report, path_to_index, random_lengths
 
 pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
@@ -54,6 +54,19 @@ def test_neg_cent_vs_fp32_expression(oracle, impl, shape):
             _check(ours.double(), ref64)
     finally:
         vits_b200._lib.lib().mas_set_neg_cent_impl(-1)
+
+
+@pytest.mark.parametrize("shape", [(64, 192, 1024, 192), (32, 192, 1536, 256), (8, 192, 4096, 512)], ids=["c2", "c3", "c4"])
+def test_neg_cent_full_config_shapes(oracle, shape):
+    """BASELINE.json configs[1..3] at full size (c4: T_x = 512 = two column tiles, T_y = 4096 = 32 frame tiles),
+    variable lengths with zeroed padding, automatic implementation (tcgen05)."""
+    import vits_b200
+    B, C, T_y, T_x = shape
+    rng = np.random.default_rng(5)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    z, m, ls = _inputs(B, C, T_y, T_x, seed=T_y + T_x, t_ys=t_ys, t_xs=t_xs)
+    ours = vits_b200.neg_cent(z, m, ls)
+    _check(ours, oracle.neg_cent_torch(z, m, ls))
 
 
 def test_neg_cent_real_model_capture(oracle, synth_golden):
@@ -158,6 +171,10 @@ def test_end_to_end_path_agreement(oracle, shape):
     valid = sum(int(a) * int(b) for a, b in zip(t_ys, t_xs))
     differing = int((got != want).sum())
     assert differing <= 1e-3 * valid, f"{differing} of {valid} cells differ"
+    # ... and wherever the two walks part, the reference's own value table shows a near-tie (core.pyx:32)
+    parts = near_tie_report(oracle, nc_ref.cpu().numpy(), nc_ours.cpu().numpy(), path_to_index(want), path_to_index(got),
+                            t_ys, t_xs)
+    assert (differing == 0) == (len(parts) == 0)
     # and on the *same* neg_cent the paths are bit-identical
     same = vits_b200.maximum_path_from_lengths(nc_ref, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
     np.testing.assert_array_equal(same.cpu().numpy().astype(np.int32), want)

@@ -164,3 +164,24 @@ def test_low_precision_rounding_helper_matches_torch(oracle):
     t = torch.from_numpy(a)
     np.testing.assert_array_equal(oracle._round_to(a, "bfloat16"), t.to(torch.bfloat16).float().numpy())
     np.testing.assert_array_equal(oracle._round_to(a, "float16"), t.to(torch.float16).float().numpy())
+
+
+def test_near_tie_report_accepts_perturbation_sized_gaps_only(oracle):
+    """tests/helpers.near_tie_report (the end-to-end gate's confinement check): tiny input perturbations may only move
+    the walk at near-ties; a large perturbation is reported as a real disagreement."""
+    from helpers import near_tie_report, path_to_index
+    rng = np.random.default_rng(3)
+    B, T_y, T_x = 4, 300, 60
+    nc = (rng.standard_normal((B, T_y, T_x)) * 20 - 400).astype(np.float32)
+    t_ys = np.array([300, 280, 200, 150], np.int32)
+    t_xs = np.array([60, 50, 44, 30], np.int32)
+    ref = path_to_index(oracle.maximum_path_numpy(nc, t_ys, t_xs))
+    small = (nc.astype(np.float64) * (1 + 2e-6 * rng.standard_normal(nc.shape))).astype(np.float32)
+    got = path_to_index(oracle.maximum_path_numpy(small, t_ys, t_xs))
+    near_tie_report(oracle, nc, small, ref, got, t_ys, t_xs)          # must not raise
+    assert near_tie_report(oracle, nc, nc, ref, ref, t_ys, t_xs) == []
+    # a path that differs although the inputs are IDENTICAL is never a near-tie (bound = rounding only)
+    other = path_to_index(oracle.maximum_path_numpy(nc + rng.standard_normal(nc.shape).astype(np.float32) * 30, t_ys, t_xs))
+    assert (other != ref).any()
+    with pytest.raises(AssertionError):
+        near_tie_report(oracle, nc, nc, ref, other, t_ys, t_xs)

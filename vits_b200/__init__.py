@@ -14,7 +14,8 @@ Public surface:
 """
 from . import _lib  # noqa: F401
 from . import monotonic_align  # noqa: F401
-from .monotonic_align import maximum_path, maximum_path_from_lengths, maximum_path_index  # noqa: F401
+from .monotonic_align import (last_status, maximum_path, maximum_path_from_lengths, maximum_path_index,  # noqa: F401
+                              status_nosync)
 from .neg_cent import maximum_path_from_stats, neg_cent  # noqa: F401
 from . import shard  # noqa: F401
 from .alignment_ops import expand_prior, generate_path, kl_loss_from_index, path_durations  # noqa: F401

@@ -2,6 +2,7 @@
 Each .cu is compiled to an object in parallel, then linked."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -32,11 +33,28 @@ def _deps():
         os.path.join(os.path.dirname(_HERE), "include", "vits_mas.h")]
 
 
+STAMP = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """Digest of every source the library is built from (content, not mtimes: a snapshot copied to another
+    box keeps its contents but not necessarily its timestamps)."""
+    h = hashlib.sha256()
+    for d in sorted(_deps()):
+        if d.endswith((".cu", ".cuh", ".h")):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True when libvits_mas.so is missing or was built from other sources than the ones in csrc/ now."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def _compile_one(nvcc, src, obj, verbose):
@@ -56,6 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in srcs:
         src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
         stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), headers_mtime)
+        stale = stale or not os.path.exists(STAMP)
         jobs.append((src, obj, stale))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         results = list(ex.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose) if j[2] else (None, None), jobs))
@@ -73,6 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if out.returncode != 0:
         print(out.stdout, out.stderr)
         raise RuntimeError("linking libvits_mas.so failed")
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

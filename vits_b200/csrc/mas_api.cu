@@ -1,6 +1,7 @@
 // mas_api.cu -- the extern "C" surface declared in include/vits_mas.h, plus the host-buffer
 // entry that mirrors the reference's native call maximum_path_c (monotonic_align/core.pyx:38).
 #include <atomic>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
@@ -12,11 +13,42 @@
 namespace mas {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// One pinned, portable, device-mapped allocation for every device: [kMaxDevices][4] int32, word k of a device's
+// row = "MAS_STATUS bit k was raised".  With unified addressing the host pointer is valid on every device.
+static std::atomic<int32_t*> g_mirror{nullptr};
+static std::atomic<int> g_mirror_state{0};  // 0 untried, 1 ready, 2 unavailable
+static int32_t* mirror_base() {
+  int st = g_mirror_state.load(std::memory_order_acquire);
+  if (st == 0) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    st = g_mirror_state.load(std::memory_order_acquire);
+    if (st == 0) {
+      void* p = nullptr;
+      const cudaError_t e = cudaHostAlloc(&p, kMaxDevices * 4 * sizeof(int32_t), cudaHostAllocPortable | cudaHostAllocMapped);
+      if (e == cudaSuccess && p) {
+        memset(p, 0, kMaxDevices * 4 * sizeof(int32_t));
+        g_mirror.store(static_cast<int32_t*>(p), std::memory_order_release);
+        st = 1;
+      } else {
+        cudaGetLastError();  // (e.g. inside a stream capture: try again on a later call)
+        return nullptr;
+      }
+      g_mirror_state.store(st, std::memory_order_release);
+    }
+  }
+  return st == 1 ? g_mirror.load(std::memory_order_acquire) : nullptr;
+}
+int32_t* status_mirror() {
+  int32_t* base = mirror_base();
+  return base ? base + 4 * current_device() : nullptr;
+}
 }  // namespace mas
 
 namespace {
 
-// State cached by the host entry (single caller thread, like the reference).
+// State cached by the host entry, one per device (single caller thread per device, like the reference).
 struct HostCtx {
   static constexpr int kChunks = 32;  // most utterance groups pipelined over PCIe
   static constexpr int kStreams = 4;
@@ -27,9 +59,11 @@ struct HostCtx {
   void* d_scratch = nullptr;
   cudaEvent_t ev_in[kChunks] = {}, ev_k[kChunks] = {};  // group c: inputs landed / kernels done
   int32_t* h_status = nullptr;  // pinned, kChunks words
-  size_t cap_cells = 0, cap_lens = 0, cap_scratch = 0;
+  size_t cap_cells = 0, cap_path_bytes = 0, cap_lens = 0, cap_scratch = 0;
   bool ready = false;
-} g_host;
+};
+HostCtx g_hosts[mas::kMaxDevices];
+#define g_host (g_hosts[mas::current_device()])
 
 void host_release() {
   if (g_host.d_values) cudaFree(g_host.d_values);
@@ -52,7 +86,7 @@ void host_release() {
     if (e_ != cudaSuccess) return static_cast<int>(e_); \
   } while (0)
 
-int host_prepare(size_t cells, size_t lens, size_t scratch) {
+int host_prepare(size_t cells, size_t lens, size_t scratch, int path_es) {
   if (!g_host.ready) {
     for (auto& s : g_host.streams) MAS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto& e : g_host.ev_in) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -63,12 +97,17 @@ int host_prepare(size_t cells, size_t lens, size_t scratch) {
   }
   if (cells > g_host.cap_cells) {
     if (g_host.d_values) cudaFree(g_host.d_values);
-    if (g_host.d_paths) cudaFree(g_host.d_paths);
-    g_host.d_values = g_host.d_paths = nullptr;
+    g_host.d_values = nullptr;
     g_host.cap_cells = 0;
     MAS_CUDA(cudaMalloc(&g_host.d_values, cells * 4));
-    MAS_CUDA(cudaMalloc(&g_host.d_paths, cells * 4));
     g_host.cap_cells = cells;
+  }
+  if (cells * path_es > g_host.cap_path_bytes) {
+    if (g_host.d_paths) cudaFree(g_host.d_paths);
+    g_host.d_paths = nullptr;
+    g_host.cap_path_bytes = 0;
+    MAS_CUDA(cudaMalloc(&g_host.d_paths, cells * path_es));
+    g_host.cap_path_bytes = cells * path_es;
   }
   if (lens > g_host.cap_lens) {
     if (g_host.d_lens) cudaFree(g_host.d_lens);
@@ -91,7 +130,9 @@ int host_prepare(size_t cells, size_t lens, size_t scratch) {
 
 extern "C" {
 
-int mas_abi_version(void) { return 1; }
+int mas_abi_version(void) { return 2; }
+
+int32_t* mas_status_mirror(void) { return mas::status_mirror(); }
 
 const char* mas_error_string(int code) {
   switch (code) {
@@ -124,8 +165,8 @@ int mas_maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* 
 // utterances are about equally long.  (One copy per utterance moved fewer bytes but was slower: 128 small
 // copies per call cost more host time than the PCIe time they saved.)
 static cudaError_t copy_leading_rows(void* dst, const void* src, const int32_t* t_ys, int b0, int nb, int T_y, int T_x,
-                                     cudaMemcpyKind kind, cudaStream_t st) {
-  const size_t plane = static_cast<size_t>(T_y) * T_x * 4;
+                                     cudaMemcpyKind kind, cudaStream_t st, int es = 4) {
+  const size_t plane = static_cast<size_t>(T_y) * T_x * es;
   int rows = 0;
   for (int b = b0; b < b0 + nb; ++b) rows = t_ys[b] > rows ? t_ys[b] : rows;
   rows = rows > T_y ? T_y : rows;
@@ -133,13 +174,38 @@ static cudaError_t copy_leading_rows(void* dst, const void* src, const int32_t* 
   char* d = static_cast<char*>(dst) + plane * b0;
   const char* s = static_cast<const char*>(src) + plane * b0;
   if (rows == T_y) return cudaMemcpyAsync(d, s, plane * nb, kind, st);
-  return cudaMemcpy2DAsync(d, plane, s, plane, static_cast<size_t>(rows) * T_x * 4, nb, kind, st);
+  return cudaMemcpy2DAsync(d, plane, s, plane, static_cast<size_t>(rows) * T_x * es, nb, kind, st);
 }
+
+static int path_elem_size(int dtype) {
+  switch (dtype) {
+    case MAS_F32: case MAS_I32: return 4;
+    case MAS_F16: case MAS_BF16: case MAS_I16: return 2;
+    case MAS_F64: case MAS_I64: return 8;
+    case MAS_U8: case MAS_I8: return 1;
+    default: return 0;
+  }
+}
+
+static int host_run(void* paths, int path_dtype, int zero_tail, const float* values, const int32_t* t_ys,
+                    const int32_t* t_xs, int B, int T_y, int T_x);
 
 int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs, int B,
                             int T_y, int T_x) {
+  return host_run(paths, MAS_I32, 0, values, t_ys, t_xs, B, T_y, T_x);
+}
+
+int mas_maximum_path_host(void* paths, int path_dtype, int zero_tail, const float* values, const int32_t* t_ys,
+                          const int32_t* t_xs, int B, int T_y, int T_x) {
+  return host_run(paths, path_dtype, zero_tail, values, t_ys, t_xs, B, T_y, T_x);
+}
+
+static int host_run(void* paths, int path_dtype, int zero_tail, const float* values, const int32_t* t_ys,
+                    const int32_t* t_xs, int B, int T_y, int T_x) {
   if (B <= 0 || T_y <= 0 || T_x <= 0) return MAS_E_BAD_SHAPE;
   if (!paths || !values || !t_ys || !t_xs) return MAS_E_NULL;
+  const int es = path_elem_size(path_dtype);
+  if (es == 0) return MAS_E_BAD_DTYPE;
   const size_t plane = static_cast<size_t>(T_y) * T_x;
   // Groups of about 12 MB: enough of them to overlap the two copy directions and the kernels, few enough
   // that the ~11 driver calls per group stay off the critical path (c2, 2 x 50 MB: 4 groups 46.4k
@@ -182,11 +248,11 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
   }
   const size_t sc_one = (mas::maximum_path_scratch_bytes(per, T_y, T_x) + 255) & ~size_t(255);
   if (sc_one == 0) return MAS_E_BAD_SHAPE;
-  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * ng);
+  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * ng, es);
   if (rc != MAS_OK) return rc;
 
   float* d_values = static_cast<float*>(g_host.d_values);
-  int32_t* d_paths = static_cast<int32_t*>(g_host.d_paths);
+  unsigned char* d_paths = static_cast<unsigned char*>(g_host.d_paths);
   int32_t* d_ty = static_cast<int32_t*>(g_host.d_lens);
   int32_t* d_tx = d_ty + B;
   // One stream feeds the inputs group by group without ever waiting for anything (H2D copy engine busy
@@ -206,16 +272,29 @@ int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* 
     MAS_CUDA(copy_leading_rows(d_values, values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
     MAS_CUDA(cudaEventRecord(g_host.ev_in[c], s_in));
     MAS_CUDA(cudaStreamWaitEvent(s_k, g_host.ev_in[c], 0));
-    rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0,
-                           MAS_I32, nullptr, sc, sc_one, nb, T_y, T_x, s_k);
+    rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0 * es,
+                           path_dtype, nullptr, sc, sc_one, nb, T_y, T_x, s_k);
     if (rc != MAS_OK) {
       for (auto& s : g_host.streams) cudaStreamSynchronize(s);
       return rc;
     }
     MAS_CUDA(cudaEventRecord(g_host.ev_k[c], s_k));
     MAS_CUDA(cudaStreamWaitEvent(s_out, g_host.ev_k[c], 0));
-    MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out));
+    MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out, es));
     nused = c + 1;
+  }
+  if (zero_tail) {
+    // the rows no copy writes (at or beyond the longest utterance of each group), zeroed on the host while the
+    // copies are in flight: the caller may then hand in an uninitialised buffer (no np.zeros pass of its own)
+    for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
+      int rows = 0;
+      for (int b = b0; b < b0 + gsize[c]; ++b) rows = t_ys[b] > rows ? t_ys[b] : rows;
+      rows = rows > T_y ? T_y : (rows < 0 ? 0 : rows);
+      if (rows == T_y) continue;
+      for (int b = b0; b < b0 + gsize[c]; ++b)
+        memset(static_cast<unsigned char*>(paths) + (plane * b + static_cast<size_t>(rows) * T_x) * es, 0,
+               static_cast<size_t>(T_y - rows) * T_x * es);
+    }
   }
   // the status word of every group (first word of its scratch) in one strided copy
   MAS_CUDA(cudaMemcpy2DAsync(g_host.h_status, sizeof(int32_t),

@@ -77,6 +77,30 @@ __device__ __forceinline__ void mask_sums(const void* p, int dtype, int64_t off,
   }
 }
 
+// Sticky status bits: the word in the scratch (device) and, when there is one, the host-mapped mirror (one word
+// per bit, plain stores: no PCIe atomics needed).  Error paths only.
+__device__ __forceinline__ void raise_status(int32_t* word, int32_t* mirror, int bits) {
+  atomicOr(word, bits);
+  if (mirror) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((bits >> k) & 1) *reinterpret_cast<volatile int32_t*>(mirror + k) = 1;
+    __threadfence_system();
+  }
+}
+
+// Streaming hand-off of decision words between kernels: {word, tag} travels as ONE 64-bit scalar (word in the low
+// half), so a reader that sees the tag also sees the word -- a 64-bit aligned scalar access is single-copy atomic in
+// the PTX memory model, and a vector store/load is a sequence of such scalars (a 2 x 32-bit vector would formally be
+// two independent 32-bit accesses).
+__device__ __forceinline__ unsigned long long pack_tagged(uint32_t word, uint32_t tag) {
+  return static_cast<unsigned long long>(word) | (static_cast<unsigned long long>(tag) << 32);
+}
+__device__ __forceinline__ uint2 load_tagged(const uint2* p) {
+  const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+  return make_uint2(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

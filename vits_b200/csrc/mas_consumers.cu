@@ -108,12 +108,8 @@ int expand_prior(const int32_t* index, const float* m_p, const float* logs_p, fl
   if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || B > 65535) return MAS_E_BAD_SHAPE;
   if (!index || !m_p || !m_out || ((logs_p == nullptr) != (logs_out == nullptr))) return MAS_E_NULL;
   const size_t smem = static_cast<size_t>(logs_p ? 2 : 1) * kCPB * T_x * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mas_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  if (cudaError_t e = ensure_dyn_smem(mas_expand_kernel, 160 * 1024, attr); e != cudaSuccess) return static_cast<int>(e);
   mas_expand_kernel<<<dim3(B, (C + kCPB - 1) / kCPB), 256, smem, st>>>(index, m_p, logs_p, m_out, logs_out, C, T_y, T_x);
   count_launch();
   return static_cast<int>(cudaGetLastError());
@@ -196,12 +192,8 @@ int kl_from_index(const int32_t* index, const float* z_p, const float* logs_q, c
   if (B <= 0 || C <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || B > 65535) return MAS_E_BAD_SHAPE;
   if (!index || !z_p || !logs_q || !m_p || !logs_p || !z_mask || !out) return MAS_E_NULL;
   const size_t smem = static_cast<size_t>(2) * kCPB * T_x * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(mas_kl_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  if (cudaError_t e0 = ensure_dyn_smem(mas_kl_index_kernel, 160 * 1024, attr); e0 != cudaSuccess) return static_cast<int>(e0);
   cudaError_t e = cudaMemsetAsync(out, 0, 2 * sizeof(double), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   mas_kl_index_kernel<<<dim3(B, (C + kCPB - 1) / kCPB), 256, smem, st>>>(index, z_p, logs_q, m_p, logs_p, z_mask, out, C, T_y, T_x);

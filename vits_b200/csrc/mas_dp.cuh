@@ -44,6 +44,7 @@ struct DpParams {
   int64_t msb, msy, msx;
   int32_t* lens;         // [B][2] = (t_y, t_x), (0,0) when invalid
   int32_t* status;       // sticky MAS_STATUS_* bits
+  int32_t* mirror;       // host-mapped copy (one word per bit) or nullptr
   int32_t* wo_counters;  // the fill kernel's two work counters; zeroed here before it may start
   uint32_t* bits;        // [B][G][TXP] decision words: bit (31-r) of word [g][x] = "step left when leaving frame 32g+r";
                          // streaming mode: [B][G][TXP] pairs {word, tag}
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
     uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
     const int n16 = p.G * p.TXP / 2;  // TXP is a multiple of 32
     for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) p.lenstag[b] = make_uint2(0u, 0u);
+    if (tid == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
   }
   if (tid == 0) tl_min(p.tl, 0);
 #ifdef MAS_TRACE
@@ -232,11 +233,11 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
     if (t_x > t_y) st |= MAS_STATUS_TX_GT_TY;
     if (st) t_y = t_x = 0;  // the path of this utterance stays all-zero
     if (lane == 0) {
-      if (st) atomicOr(p.status, st);
+      if (st) raise_status(p.status, p.mirror, st);
       p.lens[2 * b] = t_y;
       p.lens[2 * b + 1] = t_x;
       if (p.lenstag)  // streaming backtrack: the lengths are published
-        p.lenstag[b] = make_uint2((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), tag);
+        *reinterpret_cast<unsigned long long*>(p.lenstag + b) = pack_tagged((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), tag);
       lens_v[0] = t_y;
       lens_v[1] = t_x;
       __threadfence_block();
@@ -485,10 +486,10 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
         if (K % 2 == 0) {
 #pragma unroll
           for (int q = 0; q < K / 2; ++q)
-            *reinterpret_cast<uint4*>(dst + 2 * q) = make_uint4(w[2 * q], tag, w[2 * q + 1], tag);
+            ptx::st_global_v2_u64(dst + 2 * q, pack_tagged(w[2 * q], tag), pack_tagged(w[2 * q + 1], tag));
         } else {
 #pragma unroll
-          for (int jj = 0; jj < K; ++jj) dst[jj] = make_uint2(w[jj], tag);
+          for (int jj = 0; jj < K; ++jj) *reinterpret_cast<unsigned long long*>(dst + jj) = pack_tagged(w[jj], tag);
         }
       } else {
         uint32_t* dst = bits_b + static_cast<size_t>(s - Q) * p.TXP;
@@ -541,12 +542,8 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
 template <int K, int D, bool LINEAR>
 inline cudaError_t launch_dp_t(const CUtensorMap& tmap, const DpParams& p, cudaStream_t st) {
   auto kern = mas_dp_kernel<K, D, LINEAR>;
-  static bool attr_set = false;  // per instantiation; set once, never during a later stream capture
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_set{0};  // per instantiation and device
+  if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024, attr_set); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.B);
   cfg.blockDim = dim3(p.W <= 3 ? 32 * 12 : 32 * (p.W + 4 + 1));  // see the warp roles in the kernel

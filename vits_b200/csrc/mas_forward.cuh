@@ -32,6 +32,7 @@ struct FwdParams {
   int64_t msb, msy, msx;
   int32_t* lens;    // [B][2] = (t_y, t_x), (0,0) when invalid
   int32_t* status;  // sticky MAS_STATUS_* bits
+  int32_t* mirror;  // host-mapped copy (one word per bit) or nullptr
   int32_t* wo_counters;  // the write-out kernel's two work counters; zeroed here before it may start
   uint32_t* bits;   // [B][G][TXP]   (unfused mode only); streaming mode: pairs {word, tag = 1}
   uint2* lenstag;   // streaming mode: [B] {t_y << 12 | t_x, tag = 1}; else nullptr
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
     uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
     const int n16 = p.G * p.TXP / 2;  // TXP is a multiple of 32
     for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) p.lenstag[b] = make_uint2(0u, 0u);
+    if (tid == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
   }
   if (ll) __syncthreads();
   if (tid == 0 && (ll || b == 0)) __threadfence();  // (cumulative: covers the other threads' stores ordered by the barrier)
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
     if (t_x > t_y) st |= MAS_STATUS_TX_GT_TY;
     if (st) {  // whole CTA: the path of this utterance stays all-zero
       if (tid == 0) {
-        atomicOr(p.status, st);
+        raise_status(p.status, p.mirror, st);
         p.lens[2 * b] = 0;
         p.lens[2 * b + 1] = 0;
-        if (ll) p.lenstag[b] = make_uint2(0u, 1u);
+        if (ll) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = pack_tagged(0u, 1u);
         for (int c = 0; c < nspec; ++c) ptx::mbar_wait(&full[c], 0);  // no copy may outlive the CTA
       }
       if (fused)
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
   if (tid == 0) {
     p.lens[2 * b] = t_y;
     p.lens[2 * b + 1] = t_x;
-    if (ll) p.lenstag[b] = make_uint2((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), 1u);
+    if (ll) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = pack_tagged((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), 1u);
     for (int s = 0; s < S; ++s) ptx::mbar_init(&empty[s], W_act);
     for (int i = 0; i < (W - 1) * S; ++i) ptx::mbar_init(&bfull[i], 1);
     if (fused)
@@ -356,10 +357,10 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
         if (K % 2 == 0) {
 #pragma unroll
           for (int q = 0; q < K / 2; ++q)
-            *reinterpret_cast<uint4*>(d2 + 2 * q) = make_uint4(acc[2 * q] << sh, 1u, acc[2 * q + 1] << sh, 1u);
+            ptx::st_global_v2_u64(d2 + 2 * q, pack_tagged(acc[2 * q] << sh, 1u), pack_tagged(acc[2 * q + 1] << sh, 1u));
         } else {
 #pragma unroll
-          for (int j = 0; j < K; ++j) d2[j] = make_uint2(acc[j] << sh, 1u);
+          for (int j = 0; j < K; ++j) *reinterpret_cast<unsigned long long*>(d2 + j) = pack_tagged(acc[j] << sh, 1u);
         }
       } else if (K % 4 == 0) {
 #pragma unroll
@@ -574,12 +575,8 @@ __global__ void __launch_bounds__(BIG ? 1024 : 256, 1) mas_forward_kernel(const 
 template <int K, bool VEC, bool BIG, int BPC>
 inline cudaError_t launch_fwd_t(const FwdParams& p, cudaStream_t st) {
   auto kern = mas_forward_kernel<K, VEC, BIG, BPC>;
-  static bool attr_set = false;  // per instantiation; set once, never during a later stream capture
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_set{0};  // per instantiation and device
+  if (cudaError_t e = ensure_dyn_smem(kern, 200 * 1024, attr_set); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.B);
   cfg.blockDim = dim3(32 * (1 + p.W + p.H));

@@ -4,9 +4,35 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace mas {
 
 void count_launch();
+
+// ---- per-device host state (several GPUs may be driven from one process) ----
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: `done` (one static per call site) remembers
+// the devices it was applied on.  Never called for the first time during a stream capture in practice (callers
+// warm up eagerly), and legal there anyway.
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, std::atomic<uint64_t>& done) {
+  const uint64_t bit = 1ull << current_device();
+  if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_relaxed);
+  return e;
+}
+int num_sms();  // of the current device (cached per device)
+// Host-mapped status mirror of the current device: 4 int32 words, one per MAS_STATUS_* bit, that the kernels set
+// to 1 besides the sticky word in the scratch, so the host can poll for errors without synchronising.  nullptr if
+// pinned memory could not be allocated (the mirror is then simply not written).
+int32_t* status_mirror();
 
 // mas_path.cu
 int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask, int mask_dtype,

@@ -653,7 +653,7 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   float* bias = reinterpret_cast<float*>(bops + ((s.bops_bytes + 255) & ~size_t(255)));
 
   PrepParams pp{m_p, logs_p, bops, bias, B, C, T_x, s.Nt, s.NTL, s.NCB};
-  static const int g_dbg = getenv("MAS_NC_DEBUG") ? atoi(getenv("MAS_NC_DEBUG")) : 0;
+  static const int g_dbg = getenv("MAS_NC_DEBUG") ? atoi(getenv("MAS_NC_DEBUG")) : 0;  // read once (benchmark bisection hook)
   if (!(g_dbg & 256)) neg_cent_prep_kernel<<<dim3(s.NTL * (s.Nt / 16), B, s.NPB), 64, 0, st>>>(pp);  // 4 chunks x 16 columns
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -664,10 +664,7 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   tp.B = B; tp.C = C; tp.T_y = T_y; tp.T_x = T_x;
   tp.Nt = s.Nt; tp.NTL = s.NTL; tp.MT = s.MT; tp.NCB = s.NCB;
   tp.tiles = B * s.MT * s.NTL;
-  {
-    const char* d = getenv("MAS_NC_DEBUG");
-    tp.dbg = d ? atoi(d) : 0;
-  }
+  tp.dbg = g_dbg;
   static unsigned long long* d_trace = nullptr;
   if (tp.dbg & 16) {
     if (!d_trace) cudaMalloc(&d_trace, (2 + 2 * 4000) * 8);
@@ -678,17 +675,10 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   tp.ZS = tc::ZS_MAX;
   while (tp.ZS > 1 && fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE > 225 * 1024) --tp.ZS;
   const size_t smem = fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE + ((tp.dbg & 16) ? (4 * 200 * 16 + 64) : 0);
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
-    e = cudaFuncSetAttribute(neg_cent_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr{0};
+  e = ensure_dyn_smem(neg_cent_tc_kernel, 227 * 1024, attr);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int sms = num_sms();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tp.tiles < sms ? tp.tiles : sms);
   cfg.blockDim = dim3(tc::N_WARPS * 32);

@@ -232,6 +232,7 @@ struct BsParams {
   int TXS;                  // shared-memory row stride in words (odd)
   int cols_per_warp;        // 32*K of the forward kernel: ceil(t_x / cols_per_warp) warps arrive per group
   int32_t* status;          // sticky MAS_STATUS_* bits (MAS_STATUS_TIMEOUT: a poll below gave up)
+  int32_t* mirror;          // host-mapped copy of the status bits (one word per bit) or nullptr
   int dec16;                // 1: tables hold 16-bit exit columns (long utterances), the per-frame index is re-walked from the words
   int es;
   unsigned long long one;
@@ -291,21 +292,27 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
   uint16_t* sexit = reinterpret_cast<uint16_t*>(smem);                      // ... [G][TXS] exit columns (dec16)
   uint32_t* sstage = sdec + ((static_cast<size_t>(p.G) * p.TXS) >> (p.dec16 ? 1 : 0)) + 1;  // [nw][TXS] a group's words
   int* sentry = reinterpret_cast<int*>(sstage + static_cast<size_t>(nw) * p.TXS);  // [G]
-  int* smisc = sentry + p.G;                                                // [4]: t_y, t_x, entry below the top group, tag
+  int* smisc = sentry + p.G;                                                // [5]: t_y, t_x, entry below the top group, top decisions, timed out
 
   ptx::pdl_launch_dependents();  // the next call's forward kernel may set up while we run
   if (tid == 0) tl_min(p.tl, 3);
   // Watchdog: everything this kernel polls is produced by EARLIER kernels of the stream, so a poll can only
-  // fail to terminate if one of them died; give up after 2 s (status bit, garbage result) rather than hang.
+  // fail to terminate if one of them died (or the context was descheduled for seconds).  Give up after 2 s rather
+  // than hang -- and never emit a path built from words that did not arrive: the utterance keeps an all-zero path
+  // and index -1, MAS_STATUS_TIMEOUT is raised in the scratch word AND in the host-mapped mirror, where the host
+  // side sees it on its next call without synchronising (vits_b200 raises MasError then).
   const unsigned long long t_start = globaltimer_ns();
+  volatile int* dead = smisc + 4;
+  if (tid == 0) *dead = 0;
   auto expired = [&]() {
     if (globaltimer_ns() - t_start < 2000000000ull) return false;
-    atomicOr(p.status, MAS_STATUS_TIMEOUT);
+    raise_status(p.status, p.mirror, MAS_STATUS_TIMEOUT);
+    *dead = 1;
     return true;
   };
   if (tid == 0) {
     uint2 lt;
-    while ((lt = __ldcg(p.lenstag + b)).y != 1u) {
+    while ((lt = load_tagged(p.lenstag + b)).y != 1u) {
       if (expired()) {
         lt = make_uint2(0u, 1u);
         break;
@@ -345,10 +352,10 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
       // whole rows would saturate the L2 -- then read the row and check every tag.
       for (;;) {
         bool ok = true;
-        if (lane < nfw) ok = __ldcg(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
+        if (lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
         if (__all_sync(0xffffffffu, ok)) {
           for (int x = lane; x < t_x; x += 32) {
-            const uint2 el = __ldcg(row + x);
+            const uint2 el = load_tagged(row + x);
             stage[x] = el.x;
             ok = ok && el.y == tag;
           }
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
       for (;;) {
         bool ok = true;
         if (col >= 0) {
-          const uint2 el = __ldcg(row + col);
+          const uint2 el = load_tagged(row + col);
           w = el.x;
           ok = el.y == tag;
         }
@@ -403,6 +410,12 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     }
   }
   __syncthreads();  // all tables are in shared memory
+  if (*dead) {  // a poll gave up: nothing derived from incomplete words leaves this kernel
+    if (idx_b)
+      for (int y = tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
+    finish();
+    return;
+  }
   if (warp == 0) {
     // chain over the groups below the top one: entry - popc(decisions)
     int cur = smisc[2];
@@ -422,6 +435,12 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     }
   }
   __syncthreads();
+  if (*dead) {  // (the zero-fill never completed)
+    if (idx_b)
+      for (int y = tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
+    finish();
+    return;
+  }
   // per-frame index: entry of the frame's group minus the steps taken above the frame
   unsigned char* path_b = p.path ? p.path + static_cast<size_t>(b) * p.T_y * p.T_x * p.es : nullptr;
   if (!p.dec16) {
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
         const int y = (g << 5) + r;
         if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + cur) * p.es, p.es, p.one);
         if (idx_b) idx_b[y] = cur;
-        const uint32_t bit = (g == g_top) ? (topw >> r) & 1u : (__ldcg(row + cur).x >> (31 - r)) & 1u;
+        const uint32_t bit = (g == g_top) ? (topw >> r) & 1u : (load_tagged(row + cur).x >> (31 - r)) & 1u;
         cur -= static_cast<int>(bit);
       }
     }
@@ -464,7 +483,8 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
 static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
 static int g_tune_wf = -1, g_tune_ring = 0, g_tune_wfS = 0, g_tune_wfK = 0;  // wavefront forward kernel (mas_set_tuning3)
 static int g_fill_div = 4;  // streaming mode: fill CTAs = g_fill_div/4 x SM count (tunable through MAS_FILL_DIV)
-static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only)
+static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only); bit3: skip the
+                                 // wavefront forward kernel but keep the streaming backtrack (exercises its watchdog in the tests)
 static unsigned long long* g_timeline = nullptr;
 static unsigned long long* g_trace = nullptr;
 
@@ -710,7 +730,16 @@ static unsigned long long one_bits(int dtype) {
   }
 }
 
-static int g_num_sms = 0;
+int num_sms() {
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
+}
 
 int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask, int mask_dtype,
                  int64_t msb, int64_t msy, int64_t msx, void* path_out, int path_dtype, int32_t* index_out,
@@ -728,13 +757,13 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     return MAS_E_ALIGN;
   const Layout L = scratch_layout(B, T_y, T_x);
   if (scratch_bytes < L.total) return MAS_E_SCRATCH;
-  if (g_num_sms == 0) {
-    if (const char* fd = getenv("MAS_FILL_DIV")) g_fill_div = atoi(fd) > 0 ? atoi(fd) : g_fill_div;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  static const int fill_div_env = [] {
+    const char* fd = getenv("MAS_FILL_DIV");  // benchmark hook
+    return fd && atoi(fd) > 0 ? atoi(fd) : 0;
+  }();
+  if (fill_div_env) g_fill_div = fill_div_env;
+  const int g_num_sms = num_sms();
+  int32_t* mirror = status_mirror();
   // Backtrack mode (mas_set_tuning2): 2 = streaming kernel on the idle SMs while the forward kernel runs
   // (per-group tables of every group + one staging row per warp must fit in its shared memory), 1 = fused
   // into the forward kernel (helper warps), 0 = separate kernel after the forward kernel.
@@ -780,7 +809,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     DpParams dp{};
     dp.nc = neg_cent; dp.t_ys = t_ys; dp.t_xs = t_xs;
     dp.mask = mask; dp.mask_dtype = mask_dtype; dp.msb = msb; dp.msy = msy; dp.msx = msx;
-    dp.lens = lens; dp.status = status; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
+    dp.lens = lens; dp.status = status; dp.mirror = mirror; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
     dp.wo_counters = status + 4;
     dp.pdl = g_tune_pdl == 2;  // see set_tuning: the forward kernel is an ordinary launch by default
     dp.B = B; dp.T_y = T_y; dp.T_x = T_x;
@@ -790,14 +819,16 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     dp.use_tma = ((reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0) ? 1 : 0;
     if (dp.use_tma && !make_tensor_map(&tmap, neg_cent, static_cast<long long>(B) * T_y, T_x, kRows, 32 * dc.K))
       dp.use_tma = 0;
-    e = launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    count_launch();
+    if (!(g_debug_kernels & 8)) {  // (bit 3: watchdog test hook -- the backtrack kernel then never gets its words)
+      e = launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      count_launch();
+    }
   } else if (g_debug_kernels & 1) {
     FwdParams fp{};
     fp.nc = neg_cent; fp.t_ys = t_ys; fp.t_xs = t_xs;
     fp.mask = mask; fp.mask_dtype = mask_dtype; fp.msb = msb; fp.msy = msy; fp.msx = msx;
-    fp.lens = lens; fp.status = status; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
+    fp.lens = lens; fp.status = status; fp.mirror = mirror; fp.bits = bits; fp.index = index; fp.tl = g_timeline;
     fp.lenstag = stream ? lenstag : nullptr;
     fp.wo_counters = status + 4;
     fp.pdl = g_tune_pdl == 2;
@@ -823,12 +854,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     if (GS < 1) return MAS_E_UNSUPPORTED;
     bp.GS = GS;
     const size_t bt_smem = static_cast<size_t>(bp.GS) * bp.TXS * 6 + (bp.GS + 1) * 4 + static_cast<size_t>(bp.GS) * 32 * 4 + 64;
-    static bool bt_attr = false;
-    if (!bt_attr) {
-      e = cudaFuncSetAttribute(mas_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      bt_attr = true;
-    }
+    static std::atomic<uint64_t> bt_attr{0};
+    e = ensure_dyn_smem(mas_backtrack_kernel, 200 * 1024, bt_attr);
+    if (e != cudaSuccess) return static_cast<int>(e);
     long long tasks = static_cast<long long>(bp.GS) * T_x;
     int threads = tasks >= 1024 ? 1024 : static_cast<int>((tasks + 31) / 32 * 32);
     if (threads < 64) threads = 64;
@@ -863,12 +891,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     // with a forward CTA; they still pack several per SM on the SMs the forward kernel leaves idle.
     long long wo_smem = 229LL * 1024 - fwd_smem;
     if (wo_smem < 0 || wo_smem > 56 * 1024) wo_smem = 0;  // forward CTA too small to exclude cheaply
-    static bool wo_attr = false;
-    if (!wo_attr) {
-      e = cudaFuncSetAttribute(mas_writeout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      wo_attr = true;
-    }
+    static std::atomic<uint64_t> wo_attr{0};
+    e = ensure_dyn_smem(mas_writeout_kernel, 64 * 1024, wo_attr);
+    if (e != cudaSuccess) return static_cast<int>(e);
     e = launch_pdl(mas_writeout_kernel, dim3(grid), dim3(256), static_cast<size_t>(wo_smem), st, wp);
     if (e != cudaSuccess) return static_cast<int>(e);
     count_launch();
@@ -879,7 +904,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   // then simply find everything ready.
   if (stream) {
     BsParams sp{};
-    sp.bits = reinterpret_cast<const uint2*>(bits); sp.lenstag = lenstag; sp.status = status;
+    sp.bits = reinterpret_cast<const uint2*>(bits); sp.lenstag = lenstag; sp.status = status; sp.mirror = mirror;
     sp.index = index_out;  // only when the caller wants it
     sp.path = (path_out && (g_debug_kernels & 4)) ? static_cast<unsigned char*>(path_out) : nullptr;
     sp.fill_counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;
@@ -893,12 +918,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     long long excl = 229LL * 1024 - fwd_smem;
     if (excl < 0 || excl > 72 * 1024) excl = 0;
     const size_t smem = bs_smem > static_cast<size_t>(excl) ? bs_smem : static_cast<size_t>(excl);
-    static bool bs_attr = false;
-    if (!bs_attr) {
-      e = cudaFuncSetAttribute(mas_backtrack_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      bs_attr = true;
-    }
+    static std::atomic<uint64_t> bs_attr{0};
+    e = ensure_dyn_smem(mas_backtrack_stream_kernel, 200 * 1024, bs_attr);
+    if (e != cudaSuccess) return static_cast<int>(e);
     e = launch_pdl(mas_backtrack_stream_kernel, dim3(B), dim3(32 * bt_warps), smem, st, sp);
     if (e != cudaSuccess) return static_cast<int>(e);
     count_launch();

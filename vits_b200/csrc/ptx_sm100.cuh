@@ -91,6 +91,9 @@ __device__ __forceinline__ void st_volatile_f32(float* p, float v) {
 __device__ __forceinline__ void st_volatile_s32(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_global_v2_u64(void* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

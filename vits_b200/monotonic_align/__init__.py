@@ -24,7 +24,8 @@ import torch
 
 from .. import _lib
 
-__all__ = ["maximum_path", "maximum_path_index", "maximum_path_from_lengths", "last_status", "StatusError"]
+__all__ = ["maximum_path", "maximum_path_index", "maximum_path_from_lengths", "last_status", "status_nosync",
+           "StatusError"]
 
 _DT = {
     torch.float32: _lib.MAS_F32, torch.float16: _lib.MAS_F16, torch.bfloat16: _lib.MAS_BF16,
@@ -44,10 +45,45 @@ def _scratch_for(device: torch.device, stream: int, nbytes: int) -> torch.Tensor
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
-        # zero-initialised: the first word is the sticky status word
-        buf = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-        _scratch[key] = buf
+        # zero-initialised: the first word is the sticky status word (carried over when the buffer grows)
+        new = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        if buf is not None:
+            new[:4].copy_(buf[:4])
+        _scratch[key] = buf = new
     return buf
+
+
+def _mirror(device: torch.device):
+    """The library's host-mapped status words of `device` (ctypes int32[4]) or None."""
+    with torch.cuda.device(device):
+        p = _lib.lib().mas_status_mirror()
+    return p if p else None
+
+
+def status_nosync(device=None, reset: bool = False) -> int:
+    """MAS_STATUS_* bits raised by any call on ``device`` so far, read from the library's host-mapped mirror:
+    no synchronisation, no copy (bits of kernels still in flight show up once they have run).  The dense status
+    word read by :func:`last_status` is per stream and needs a sync; this one is what a training loop can poll
+    every step."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    m = _mirror(dev)
+    if m is None:
+        return 0
+    bits = sum((1 << k) for k in range(4) if m[k])
+    if reset:
+        for k in range(4):
+            m[k] = 0
+    return bits
+
+
+def _raise_if_timed_out(dev: torch.device) -> None:
+    """A kernel of an EARLIER call gave up waiting (MAS_STATUS_TIMEOUT): that call's affected utterances got an
+    all-zero path.  Fail loudly now rather than let training continue on it."""
+    m = _mirror(dev)
+    if m is not None and m[3]:
+        m[3] = 0
+        raise _lib.MasError("an earlier maximum_path call on this device timed out waiting for one of its own kernels "
+                            "(MAS_STATUS_TIMEOUT): its alignment is all-zero for the affected utterances and must not be used")
 
 
 def _decode_status(bits: int) -> str:
@@ -98,6 +134,7 @@ def _run_cuda(neg_cent: torch.Tensor, *, mask: Optional[torch.Tensor], t_ys: Opt
         values = values.float()  # the reference always computes in float32 (__init__.py:14)
     out_dtype = neg_cent.dtype
     with torch.cuda.device(dev):
+        _raise_if_timed_out(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         nbytes = int(L.mas_maximum_path_scratch_bytes(B, T_y, T_x))
         scratch = _scratch_for(dev, stream, nbytes)
@@ -148,14 +185,17 @@ def _run_host(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch.Tensor, ch
         values = values.float()
     t_ys = t_ys.to(torch.int32).contiguous()
     t_xs = t_xs.to(torch.int32).contiguous()
-    paths = torch.zeros((B, T_y, T_x), dtype=torch.int32)  # np.zeros, __init__.py:15: padded rows are never written
-    rc = L.mas_maximum_path_c_host(paths.data_ptr(), values.data_ptr(), t_ys.data_ptr(), t_xs.data_ptr(), B, T_y, T_x)
+    # the path leaves the device already in neg_cent's dtype (no int32 -> float pass on the host, __init__.py:20), and
+    # the entry zeroes the padded rows it does not copy (no np.zeros pass, __init__.py:15)
+    paths = torch.empty((B, T_y, T_x), dtype=neg_cent.dtype)
+    rc = L.mas_maximum_path_host(paths.data_ptr(), _DT[neg_cent.dtype], 1, values.data_ptr(), t_ys.data_ptr(),
+                                 t_xs.data_ptr(), B, T_y, T_x)
     if rc > 0 and (rc & 0xFF) == 0:
         if check or _CHECK:
             raise StatusError(_decode_status(rc >> 8))
     else:
-        _lib.check(rc, "mas_maximum_path_c_host")
-    return paths if neg_cent.dtype == torch.int32 else paths.to(neg_cent.dtype)
+        _lib.check(rc, "mas_maximum_path_host")
+    return paths
 
 
 def maximum_path(neg_cent: torch.Tensor, mask: torch.Tensor, check: bool = False) -> torch.Tensor:
