@@ -22,6 +22,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
 
 typedef void* mas_stream_t; /* cudaStream_t */
 
@@ -52,6 +55,9 @@ enum {
 
 int mas_abi_version(void);
 const char* mas_error_string(int code);
+/* Diagnostics: source line (vits_b200/csrc/mas_path.cu) of the CUDA call that made the calling thread's last
+ * mas_maximum_path fail with a positive cudaError_t; 0 if none. */
+int mas_last_error_site(void);
 
 /* Bytes of device scratch one maximum_path call needs (direction bits, per-frame index,
  * lengths, status word).  The caller allocates it (e.g. with torch) and may reuse it across
@@ -135,6 +141,21 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                  int B, int C, int T_y, int T_x, mas_stream_t stream);
 
 /*
+ * mas_stats_to_path -- SynthesizerTrn.py:223-235 in one pass: the contraction above streamed into the alignment search
+ * (mas_maximum_path) tile by tile, so neg_cent [B,T_y,T_x] is never written to and read back from HBM between two
+ * calls -- it lives in an L2-resident ring inside `scratch` -- and the two stages overlap on disjoint SMs.  Same
+ * numerics as mas_neg_cent followed by mas_maximum_path (bit-identical paths).  z_p/m_p/logs_p as for mas_neg_cent;
+ * t_ys/t_xs device int32 [B] (x_lengths / y_lengths of SynthesizerTrn.forward -- no [B,T_y,T_x] mask is needed, :234);
+ * path_out/index_out as for mas_maximum_path (path_out required).  scratch: 256-byte aligned,
+ * >= mas_stats_to_path_scratch_bytes.  Returns MAS_E_UNSUPPORTED (nothing launched) for shapes the streamed form does
+ * not cover (T_x > 512, or B too close to the SM count): call mas_neg_cent + mas_maximum_path instead.
+ */
+size_t mas_stats_to_path_scratch_bytes(int B, int C, int T_y, int T_x);
+int mas_stats_to_path(const float* z_p, const float* m_p, const float* logs_p, const int32_t* t_ys, const int32_t* t_xs,
+                      void* path_out, int path_dtype, int32_t* index_out, void* scratch, size_t scratch_bytes,
+                      int B, int C, int T_y, int T_x, mas_stream_t stream);
+
+/*
  * mas_neg_cent_autocast -- the same contraction with the numerics the reference has AS TRAINED, inside
  * torch.autocast (train_and_evaluate.py:55, config_cje.yaml:11 fp16_run): the two einsums
  * (SynthesizerTrn.py:227, :229) take their operands rounded to `gemm_dtype` (MAS_F16 or MAS_BF16),
@@ -204,6 +225,9 @@ void mas_set_timeline(void* dev_ptr);
 /* Debug event trace of the forward kernel's CTA 0: device pointer to 8*512*2 uint64 (zeroed), or NULL. */
 void mas_set_trace(void* dev_ptr);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

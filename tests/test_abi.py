@@ -64,6 +64,16 @@ def test_argument_validation_without_gpu():
     assert L.mas_neg_cent(None, fake, fake, fake, fake, big, 1, 192, 8, 8, None) == -3
     assert L.mas_neg_cent(fake, fake, fake, fake, fake, big, 0, 192, 8, 8, None) == -1
     assert L.mas_maximum_path_c_host(None, fake, fake, fake, 1, 4, 4) == -3
+    assert L.mas_maximum_path_host(fake, 99, 0, fake, fake, fake, 1, 4, 4) == -2
+    # the streamed stats -> path entry: NULL lengths / misaligned scratch / short scratch are refused up front
+    aligned = ctypes.c_void_p(0x10000)
+    def fused(tys=fake, scratch=aligned, sbytes=big, B=2):
+        return L.mas_stats_to_path(fake, fake, fake, tys, fake, fake, _lib.MAS_F32, None, scratch, sbytes, B, 192, 64, 32, None)
+    assert fused(tys=None) == -3
+    assert fused(B=0) == -1
+    assert fused(scratch=ctypes.c_void_p(0x10010)) == -5
+    assert fused(sbytes=1024) == -4
+    assert L.mas_stats_to_path_scratch_bytes(64, 192, 1024, 192) > 64 * 1024 * 192 * 4   # holds the neg_cent ring
 
 
 def test_python_wrapper_rejects_bad_inputs():

@@ -196,3 +196,55 @@ def test_maximum_path_from_stats(oracle):
     assert torch.equal(got, want)
     idx = vits_b200.maximum_path_from_stats(z, m, ls, x_len, y_len, index=True)
     assert idx.dtype == torch.int32 and torch.equal(torch.nn.functional.one_hot(idx.clamp_min(0).long(), T_x).float() * (idx >= 0)[..., None], want)
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 130, 40), (3, 192, 260, 90), (4, 80, 300, 64), (5, 192, 700, 192),
+                                   (3, 192, 520, 300), (2, 192, 1100, 256)])
+@pytest.mark.parametrize("ragged", [True, False])
+def test_streamed_stats_to_path_is_bit_identical(oracle, shape, ragged):
+    """mas_stats_to_path (SynthesizerTrn.py:223-235 in one pass, the contraction streamed into the search through an
+    L2-resident ring) must give exactly the path of mas_neg_cent followed by mas_maximum_path, and that path must be the
+    oracle's on the identical neg_cent."""
+    import vits_b200
+    B, C, T_y, T_x = shape
+    rng = np.random.default_rng(sum(shape))
+    if ragged:
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    else:
+        t_ys, t_xs = np.full(B, T_y, np.int32), np.full(B, T_x, np.int32)
+    z, m, ls = _inputs(B, C, T_y, T_x, seed=3, t_ys=t_ys, t_xs=t_xs)
+    ty, tx = torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()
+    got = vits_b200.maximum_path_from_stats(z, m, ls, tx, ty, streamed=True)
+    idx = vits_b200.maximum_path_from_stats(z, m, ls, tx, ty, index=True, streamed=True)
+    nc = vits_b200.neg_cent(z, m, ls)
+    want = oracle.maximum_path_numpy(nc.cpu().numpy(), t_ys, t_xs)
+    np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want)
+    np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want))
+    assert got.dtype == torch.float32 and vits_b200.status_nosync() == 0
+
+
+def test_streamed_stats_to_path_bad_lengths_and_fallback(oracle):
+    import vits_b200
+    from vits_b200 import _lib
+    B, C, T_y, T_x = 4, 192, 200, 64
+    t_ys = np.array([200, 30, 150, 0], np.int32)
+    t_xs = np.array([64, 50, 40, 10], np.int32)          # utterance 1: t_x > t_y, utterance 3: empty
+    z, m, ls = _inputs(B, C, T_y, T_x, seed=5)
+    vits_b200.status_nosync(reset=True)
+    got = vits_b200.maximum_path_from_stats(z, m, ls, torch.as_tensor(t_xs), torch.as_tensor(t_ys), streamed=True)
+    torch.cuda.synchronize()
+    nc = vits_b200.neg_cent(z, m, ls).cpu().numpy()
+    ok = [0, 2]
+    want = oracle.maximum_path_numpy(nc[ok], t_ys[ok], t_xs[ok])
+    np.testing.assert_array_equal(got[ok].cpu().numpy().astype(np.int32), want)
+    assert int(got[[1, 3]].abs().sum().item()) == 0
+    bits = vits_b200.status_nosync(reset=True)
+    assert bits & _lib.MAS_STATUS_TX_GT_TY and bits & _lib.MAS_STATUS_EMPTY and not bits & _lib.MAS_STATUS_TIMEOUT
+    # a shape the streamed form does not cover falls back to the two-call path (and says so when forced)
+    z2, m2, ls2 = _inputs(1, 192, 700, 600, seed=6)
+    ty2, tx2 = torch.tensor([700]), torch.tensor([600])
+    with pytest.raises(_lib.MasError):
+        vits_b200.maximum_path_from_stats(z2, m2, ls2, tx2, ty2, streamed=True)
+    auto = vits_b200.maximum_path_from_stats(z2, m2, ls2, tx2, ty2)
+    want2 = oracle.maximum_path_numpy(vits_b200.neg_cent(z2, m2, ls2).cpu().numpy(), ty2.numpy(), tx2.numpy())
+    np.testing.assert_array_equal(auto.cpu().numpy().astype(np.int32), want2)

@@ -13,10 +13,16 @@ CSRC = os.path.join(_HERE, "csrc")
 OBJ = os.path.join(_HERE, "build")
 LIB_PATH = os.path.join(_HERE, "libvits_mas.so")
 SOURCES = ["mas_path.cu", "mas_fwd_k1.cu", "mas_fwd_k2.cu", "mas_fwd_k3.cu", "mas_fwd_k4.cu", "mas_fwd_k6.cu", "mas_fwd_k8.cu", "mas_dp_k1.cu", "mas_dp_k2.cu", "mas_dp_k4.cu", "mas_neg_cent.cu",
-           "mas_neg_cent_tc.cu", "mas_consumers.cu", "mas_api.cu"]
+           "mas_neg_cent_tc.cu", "mas_fused.cu", "mas_consumers.cu", "mas_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
+    # Nothing but the extern "C" surface is exported, and function-local statics of inline/template functions are
+    # ordinary weak symbols instead of STB_GNU_UNIQUE: a UNIQUE symbol is shared by every copy of the library in a
+    # process, and a second copy (e.g. the Cython binding's dependency next to a ctypes load of a rebuilt file) then saw
+    # "shared-memory opt-in already applied" flags that belonged to the OTHER copy's kernels -> launches failed with
+    # cudaErrorInvalidValue (r02 finding).
+    "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-fno-gnu-unique",
     "--fmad=true",   # FMA contraction is fine for neg_cent; the DP has no multiply to contract
 ]
 

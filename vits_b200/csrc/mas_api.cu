@@ -133,6 +133,7 @@ extern "C" {
 int mas_abi_version(void) { return 2; }
 
 int32_t* mas_status_mirror(void) { return mas::status_mirror(); }
+int mas_last_error_site(void) { return mas::last_fail_line(); }
 
 const char* mas_error_string(int code) {
   switch (code) {
@@ -314,6 +315,15 @@ int mas_neg_cent(const float* z_p, const float* m_p, const float* logs_p, float*
                  size_t scratch_bytes, int B, int C, int T_y, int T_x, mas_stream_t stream) {
   return mas::neg_cent(z_p, m_p, logs_p, neg_cent, scratch, scratch_bytes, B, C, T_y, T_x,
                        static_cast<cudaStream_t>(stream));
+}
+
+size_t mas_stats_to_path_scratch_bytes(int B, int C, int T_y, int T_x) { return mas::stats_to_path_scratch_bytes(B, C, T_y, T_x); }
+
+int mas_stats_to_path(const float* z_p, const float* m_p, const float* logs_p, const int32_t* t_ys, const int32_t* t_xs,
+                      void* path_out, int path_dtype, int32_t* index_out, void* scratch, size_t scratch_bytes, int B, int C,
+                      int T_y, int T_x, mas_stream_t stream) {
+  return mas::stats_to_path(z_p, m_p, logs_p, t_ys, t_xs, path_out, path_dtype, index_out, scratch, scratch_bytes, B, C, T_y,
+                            T_x, static_cast<cudaStream_t>(stream));
 }
 
 int mas_neg_cent_autocast(const float* z_p, const float* m_p, const float* logs_p, float* neg_cent, int gemm_dtype,

@@ -59,6 +59,18 @@ struct DpParams {
   int BR;       // hand-off ring length in frames (power of two)
   int use_tma;  // 1: 2-D TMA boxes (16-byte aligned base, T_x % 4 == 0); 0: 4-byte cp.async
   int pdl;
+  // Streamed mode (mas_fused.cu, SynthesizerTrn.py:223-235 in one pass): neg_cent is not a dense tensor but a
+  // per-utterance ring of RT tiles of 128 frames that the tensor-core contraction kernel (mas_neg_cent_tc.cu), running
+  // at the same time on other SMs, fills in frame order; tile_flags[b][mt] reaches tile_need once frame block mt has
+  // landed.  The tensor map then describes the ring ([B*RT*128][pitch]); chunks are requested as their tile arrives.
+  // The CTA also zero-fills its own utterance's dense path (one paced warp) and raises fill_done[b].
+  const uint32_t* tile_flags;  // nullptr = ordinary mode
+  int tile_need, RT, MT;
+  unsigned char* fill_out;     // this call's dense path [B][T_y][T_x] elements of fill_es bytes, or nullptr
+  long long fill_bytes;        // bytes per utterance
+  uint32_t* fill_done;         // [B] (stride fill_stride words), set to 1 after the fence
+  int fill_stride;
+  int fill_sleep;              // ns between bursts of four 512-byte store instructions
   DpSmem sm;
 };
 
@@ -90,7 +102,10 @@ constexpr int kRows = 32;  // frames per chunk = steps per superstep = frames pe
 // copied into slot S, so any run of 32 frames that starts inside the ring is one linear address range (a
 // per-lane base plus compile-time offsets).  Otherwise (D == 1 only; not enough shared memory for the mirror)
 // the address is selected per step between two per-lane bases.
-template <int K, int D, bool LINEAR>
+// STREAMED: neg_cent arrives tile by tile from the contraction kernel (DpParams::tile_flags).  A template parameter, not a
+// run-time flag, so that the ordinary kernel's code -- whose speed depends on its very layout in the instruction cache --
+// is exactly what it is without the streamed mode.
+template <int K, int D, bool LINEAR, bool STREAMED = false>
 __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ CUtensorMap tmap, const DpParams p) {
   static_assert(LINEAR || D == 1, "the select ring handles one chunk boundary per superstep");
   extern __shared__ __align__(128) unsigned char smem[];
@@ -126,13 +141,17 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
 
   // This kernel may have been launched programmatically behind the previous call's kernels: global
   // memory is first touched after the wait.
-  ptx::pdl_wait();
+  constexpr bool streamed = STREAMED;
+  if (!streamed) ptx::pdl_wait();  // (streamed: everything read before the tile flags is host-written or ours; see the end)
   // ---- chunk loads -----------------------------------------------------------------------------
   const long long rows_total = static_cast<long long>(p.B) * p.T_y;
   // (called by the producer warp only; w = the DP warp whose ring is filled)
   auto copy_chunk = [&](int w, int c, unsigned char* dst, uint64_t* bar) {
     if (p.use_tma) {
-      if (lane == 0) ptx::tma_load_2d(dst, &tmap, w * 32 * K, b * p.T_y + c * R, bar);
+      if (lane == 0) {
+        const int row = streamed ? b * p.RT * 128 + (c * R) % (p.RT * 128) : b * p.T_y + c * R;
+        ptx::tma_load_2d(dst, &tmap, w * 32 * K, row, bar);
+      }
     } else {
       // generic path (unaligned base or T_x % 4 != 0): every lane fetches K columns of the R frames
       // with 4-byte async copies; out-of-range cells are zero-filled like the TMA does
@@ -165,7 +184,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
   // The first two chunks of every ring are requested right away (they only need T_y as a bound; frames beyond
   // t_y are padding that exists in memory); the producer loop requests the rest -- a TMA issue costs its warp
   // up to 350 cycles, and everybody waits for the barrier below.
-  const int nspec = min(2, (p.T_y + R - 1) / R);
+  const int nspec = streamed ? 0 : min(2, (p.T_y + R - 1) / R);  // streamed: nothing exists before its tile flag says so
   if (dw == W) {
     if (lane == 0) {
       for (int i = 0; i < W * S; ++i) ptx::mbar_init(&full_all[i], p.use_tma ? 1 : 32);
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
       for (int w = 0; w < W; ++w) issue_chunk(w, c, c);
   }
 
-  if (b == 0 && tid == 0) {
+  if (!streamed && b == 0 && tid == 0) {
     p.wo_counters[0] = 0;
     p.wo_counters[1] = 0;
   }
@@ -201,8 +220,11 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
   for (int i = tid; i < (W + 1) * BR; i += blockDim.x) bnd[i] = (i == 0) ? 0.0f : kNeg;  // (0,0): v_prev = 0 (core.pyx:22-23)
   if (tid < W) prog[tid] = 0;  // supersteps completed
 
-  volatile int* lens_v = lens_s;  // [0] t_y, [1] t_x, [2] 1 once they are known
-  if (tid == 0) lens_s[2] = 0;
+  volatile int* lens_v = lens_s;  // [0] t_y, [1] t_x, [2] 1 once they are known, [3] 1 = give up (watchdog, streamed mode)
+  if (tid == 0) {
+    lens_s[2] = 0;
+    if (streamed) lens_s[3] = 0;
+  }
   __syncthreads();  // rings, barriers, hand-off arrays and flags are initialised
 
   // ---- lengths: computed by a warp of their own WHILE the DP already runs -----------------------------
@@ -244,6 +266,38 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
       lens_v[2] = 1;
       tl_max(p.tl, 7);  // (debug timeline) lengths known
     }
+    if (streamed) {
+      // This warp has nothing else to do: it zero-fills the utterance's dense path (np.zeros, __init__.py:15) with
+      // paced 16-byte stores -- 0.8 MB over the tens of microseconds the DP takes is one store instruction per ~40
+      // cycles, on the scheduler no DP warp uses -- and then publishes fill_done[b] for the backtrack kernel.
+      if (p.fill_out) {
+        unsigned char* beg = p.fill_out + static_cast<size_t>(b) * p.fill_bytes;
+        unsigned char* end = beg + p.fill_bytes;
+        unsigned char* abeg = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(beg) + 15u) & ~uintptr_t(15));
+        if (abeg > end) abeg = end;
+        unsigned char* aend = abeg + ((end - abeg) & ~ptrdiff_t(15));
+        for (unsigned char* q = beg + lane; q < abeg; q += 32) *q = 0;
+        for (unsigned char* q = aend + lane; q < end; q += 32) *q = 0;
+        uint4* a4 = reinterpret_cast<uint4*>(abeg);
+        const size_t n4 = static_cast<size_t>(aend - abeg) >> 4;
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = lane; i < n4; i += 128) {
+          a4[i] = z4;
+          if (i + 32 < n4) a4[i + 32] = z4;
+          if (i + 64 < n4) a4[i + 64] = z4;
+          if (i + 96 < n4) a4[i + 96] = z4;
+          if (p.fill_sleep) __nanosleep(p.fill_sleep);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t*>(p.fill_done + static_cast<size_t>(b) * p.fill_stride) = 1u;
+        }
+      }
+      // "this grid complete" must imply "the contraction grid complete" for whatever follows in the stream (we were
+      // launched programmatically behind it and never waited for it): wait here, where it costs nothing.
+      ptx::pdl_wait();
+    }
     return;
   }
   // the DP and producer warps learn the lengths when they are there
@@ -257,6 +311,11 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
       NS = t_y > 0 ? ((t_y - 1) >> 5) + Q + 1 : 0;
       nchunks = (t_y + R - 1) / R;
     }
+    if (streamed && lens_v[3] != 0) {  // a producer gave up waiting for the contraction kernel: wind down at once
+      known = true;
+      NS = 0;
+      nchunks = 0;
+    }
   };
   if (dw >= W) {
     // ---- producer warps (two: issuing one TMA box costs its warp 100-350 cycles, and three rings need three
@@ -267,12 +326,44 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
     int ci = nspec;        // lane w: next chunk of warp w's ring ...
     int cs = nspec % S;    // ... and its slot
     const bool mine = lane < W && (lane % NP) == q;
+    int tiles_ready = 0;  // streamed: frame blocks [0, tiles_ready) of this utterance have landed in the ring
+    unsigned long long t_wd = streamed ? globaltimer_ns() : 0ull;
     for (;;) {
       check_lens();
-      const bool want = mine && ci < nchunks;
+      bool want = mine && ci < nchunks;
+      if (streamed) {
+        // no chunk before the lengths are known (tiles past t_y are never produced) nor before its tile's flag
+        want = want && known;
+        // Tile flags are polled AHEAD of need and 32 at a time (lane l looks at frame block tiles_ready + l): one L2
+        // round trip of this warp finds every tile that has landed.  (Polling one flag when a ring ran into it cost the
+        // producer an acquire round trip + proxy fence per tile, right when its rings needed chunks: DP 47 us vs 34.)
+        const int tiles_total = known ? (lens_v[0] + 127) >> 7 : 0;
+        if (tiles_ready < tiles_total) {
+          const int mt = tiles_ready + lane;
+          const bool landed = mt < tiles_total &&
+                              ptx::ld_acquire_gpu_u32(p.tile_flags + static_cast<size_t>(b) * p.MT + mt) >= static_cast<uint32_t>(p.tile_need);
+          const unsigned lb = __ballot_sync(0xffffffffu, landed);
+          const int cnt = lb == 0xffffffffu ? 32 : __ffs(~lb) - 1;  // consecutive landed tiles from tiles_ready on
+          __syncwarp();  // the acquiring lanes' observations are ordered before lane 0's TMA requests
+          if (cnt > 0) {
+            tiles_ready += cnt;
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of the contraction kernel -> TMA reads
+            t_wd = globaltimer_ns();
+          } else if (globaltimer_ns() - t_wd > 2000000000ull) {
+            // Watchdog: the contraction kernel is an EARLIER kernel of the stream; if no tile arrives for 2 s it
+            // died.  Flag it (the host raises on its next call), wind the CTA down, leave an all-zero path.
+            if (lane == 0) {
+              raise_status(p.status, p.mirror, MAS_STATUS_TIMEOUT);
+              lens_v[3] = 1;
+            }
+            __syncwarp();
+          }
+        }
+        want = want && (ci >> 2) < tiles_ready;
+      }
       const bool ready = want && ptx::ld_volatile_s32(&prog[lane]) >= ci - S + Q + 1;
       unsigned m = __ballot_sync(0xffffffffu, ready);
-      if (known && !__any_sync(0xffffffffu, want)) break;
+      if (known && !__any_sync(0xffffffffu, mine && ci < nchunks)) break;
       if (m == 0u) __nanosleep(64);
       while (m) {
         const int w = __ffs(m) - 1;
@@ -402,6 +493,10 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
       }
       if (has_right && need_r > 0)
         while (ptx::ld_volatile_s32(&prog[dw + 1]) < need_r) {
+          if (streamed) {
+            check_lens();
+            if (NS == 0) break;
+          }
         }
       // The hand-off values are plain shared-memory loads: give their address a (null) data dependency on
       // the flag just read, or ptxas is free to hoist them above the polling loop.
@@ -539,9 +634,9 @@ __global__ void __launch_bounds__(416, 1) mas_dp_kernel(const __grid_constant__ 
 #endif
 }
 
-template <int K, int D, bool LINEAR>
+template <int K, int D, bool LINEAR, bool STREAMED = false>
 inline cudaError_t launch_dp_t(const CUtensorMap& tmap, const DpParams& p, cudaStream_t st) {
-  auto kern = mas_dp_kernel<K, D, LINEAR>;
+  auto kern = mas_dp_kernel<K, D, LINEAR, STREAMED>;
   static std::atomic<uint64_t> attr_set{0};  // per instantiation and device
   if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024, attr_set); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -560,6 +655,14 @@ inline cudaError_t launch_dp_t(const CUtensorMap& tmap, const DpParams& p, cudaS
 // skew: frames between neighbouring lanes (1..3); linear: ring with mirror slot (required for skew > 1)
 template <int K>
 inline cudaError_t launch_dp(const CUtensorMap& tmap, const DpParams& p, int skew, bool linear, cudaStream_t st) {
+  if (p.tile_flags != nullptr) {  // streamed source: linear ring only, skew 1 or 2
+    if (!linear) return cudaErrorInvalidValue;
+    switch (skew) {
+      case 1: return launch_dp_t<K, 1, true, true>(tmap, p, st);
+      case 2: return launch_dp_t<K, 2, true, true>(tmap, p, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (!linear) return skew == 1 ? launch_dp_t<K, 1, false>(tmap, p, st) : cudaErrorInvalidValue;
   switch (skew) {
     case 1: return launch_dp_t<K, 1, true>(tmap, p, st);

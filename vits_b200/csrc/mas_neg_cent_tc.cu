@@ -70,6 +70,22 @@ struct TcParams {
   int NCB;               // channel blocks = pipeline stages per tile (ceil(C/CB))
   int tiles;             // B*MT*NTL
   int ZS;                // z staging slots (3, or fewer when the column tile is wide)
+  // streamed mode (stats -> path without the HBM round trip of neg_cent, SynthesizerTrn.py:223-235): tiles are taken in
+  // FRAME-major order (all utterances' frames 0..127, then 128..255, ...) and written into a per-utterance ring of RT
+  // tiles that the concurrently running DP kernel (mas_dp.cuh) drains through L2; flags[b][mt] counts the column tiles
+  // of frame block mt that have landed.  Tiles past an utterance's length are skipped altogether.
+  int stream;            // 0: dense [B][T_y][T_x] output; 1: ring + flags
+  float* ring;           // [B][RT*128][pitch]
+  uint32_t* flags;       // [B][MT], zeroed by the prep kernel
+  const int32_t* t_ys;   // [B] device lengths (stream mode)
+  const int32_t* t_xs;
+  int RT, pitch;
+  // Two-phase schedule of the streamed mode: the grid covers EVERY SM; the first n1 * gridDim.x tiles (frame-major) are
+  // dealt round-robin to all CTAs, the rest only to the first n_long CTAs.  The other CTAs exit after their n1 tiles,
+  // and the DP kernel's CTAs (launched programmatically behind this kernel) take over their SMs: the contraction gets
+  // the whole machine until the search has enough frame blocks to start on.
+  int n_long, n1;
+  unsigned long long* tl;  // debug timeline (mas_set_timeline): slot 5 = first CTA start, slot 6 = last tile published
   int dbg;               // timing bisection only (wrong results): 1 no stores, 2 no A conversion, 4 no B copy, 8 no MMA; 16 trace; 32 no z loads; 64 no wait for prep; 128 prep only; 256 GEMM only
   unsigned long long* trace;  // dbg & 16: CTA 0 appends (tag, clock) pairs
 };
@@ -80,6 +96,7 @@ struct TcParams {
 // debug trace (dbg & 16): CTA 0, one designated lane per role appends (tag, clock) to a shared-memory
 // log (cheap: no global traffic inside the pipeline); the log is copied out at the end of the kernel.
 constexpr int kTraceCap = 200;  // events per role
+constexpr int kMaxLocalTiles = 256;  // streamed mode: tiles one CTA may own (host checks tiles / grid <= this)
 __device__ __forceinline__ void trace_ev(const TcParams& p, unsigned long long* tsm, int* tcnt, int role, int ev, int idx) {
   if ((p.dbg & 16) && blockIdx.x == 0) {
     const int k = tcnt[role];
@@ -91,6 +108,11 @@ __device__ __forceinline__ void trace_ev(const TcParams& p, unsigned long long* 
   }
 }
 
+__device__ __forceinline__ unsigned long long ptx_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_dst)),
                "r"(ncols)
@@ -180,6 +202,8 @@ struct PrepParams {
   unsigned char* bops;
   float* bias;   // [nsplit][B][NTL*Nt] partial sums over the split's channels
   int B, C, T_x, Nt, NTL, NCB;
+  uint32_t* zero_base;  // streamed mode: [B][zero_stride] words (tile flags, fill flag) cleared for this call; else nullptr
+  int zero_stride;
 };
 
 // One small CTA (64 threads) per (utterance, 16 columns of a column tile, 32-channel block); thread =
@@ -194,6 +218,8 @@ __global__ void __launch_bounds__(64) neg_cent_prep_kernel(const PrepParams p) {
   const int nt = blockIdx.x / ncg, cg = blockIdx.x - nt * ncg, b = blockIdx.y, pb = blockIdx.z;
   const int tid = threadIdx.x;
   ptx::pdl_launch_dependents();  // the GEMM kernel's A producers do not depend on us
+  if (p.zero_base != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
+    for (int i = tid; i < p.zero_stride; i += 64) p.zero_base[static_cast<size_t>(b) * p.zero_stride + i] = 0u;
   const int q = tid >> 4;              // chunk of 8 channels inside the block
   const int n = cg * 16 + (tid & 15);  // column inside the tile
   const int s0 = nt * p.Nt + n;  // text column
@@ -271,8 +297,25 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
   unsigned long long* tsm = reinterpret_cast<unsigned long long*>(sbias + 512);  // debug trace log (dbg & 16 only)
   int* tcnt = reinterpret_cast<int*>(tsm + 4 * kTraceCap * 2);
   if ((p.dbg & 16) && tid < 4) tcnt[tid] = 0;
+  __shared__ int s_ntiles;
+  __shared__ int s_tiles[kMaxLocalTiles];
 
   if (tid == 0) {
+    if (p.stream) {
+      int n = 0;
+      auto consider = [&](int tile) {
+        const int b = (tile / p.NTL) % p.B, mt = tile / (p.NTL * p.B);
+        const int ty = p.t_ys[b], tx = p.t_xs[b];
+        const bool valid = ty >= 1 && tx >= 1 && ty <= p.T_y && tx <= p.T_x && tx <= ty;  // else: all-zero path, no tiles
+        if (valid && mt * tc::M < ty && n < kMaxLocalTiles) s_tiles[n++] = tile;
+      };
+      const long long p1 = static_cast<long long>(p.n1) * gridDim.x;
+      const int phase1 = p1 < p.tiles ? static_cast<int>(p1) : p.tiles;
+      for (int tile = blockIdx.x; tile < phase1; tile += gridDim.x) consider(tile);
+      if (static_cast<int>(blockIdx.x) < p.n_long)
+        for (int tile = phase1 + blockIdx.x; tile < p.tiles; tile += p.n_long) consider(tile);
+      s_ntiles = n;
+    }
     for (int s = 0; s < tc::STAGES; ++s) {
       ptx::mbar_init(&full[s], tc::N_CV / 2 + 1);
       ptx::mbar_init(&empty[s], 1);
@@ -292,19 +335,36 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  ptx::pdl_launch_dependents();
+  if (p.stream && p.tl && tid == 0) atomicMin(p.tl + 5, ptx_globaltimer());
+  if (!p.stream) ptx::pdl_launch_dependents();
 
-  const int ntile_local = (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // Tile schedule of this CTA: tile = blockIdx.x + k * gridDim.x.  Streamed mode keeps only the tiles inside their
+  // utterance's length (compacted list in shared memory, built once by thread 0 before the barrier above).
+  const int ntile_local = p.stream ? s_ntiles : (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  auto tile_of = [&](int lt) -> int { return p.stream ? s_tiles[lt] : static_cast<int>(blockIdx.x) + lt * static_cast<int>(gridDim.x); };
+  auto decode = [&](int tile, int& b, int& mt, int& nt) {
+    nt = tile % p.NTL;
+    if (p.stream) {
+      b = (tile / p.NTL) % p.B;
+      mt = tile / (p.NTL * p.B);
+    } else {
+      mt = (tile / p.NTL) % p.MT;
+      b = tile / (p.NTL * p.MT);
+    }
+  };
 
   if (warp == tc::W_LOAD) {
     // ---------------- B loader ----------------
     if (lane == 0) {
       if (!(p.dbg & 64)) ptx::pdl_wait();  // the prep kernel's tiles must be complete
+      // Streamed mode: the dependent DP kernel may only start once the prep kernel has zeroed this call's flags,
+      // i.e. after the wait above (the ordinary mode triggers at kernel start, see below).
+      if (p.stream) ptx::pdl_launch_dependents();
       uint32_t it = 0;
       for (int lt = 0; lt < ntile_local; ++lt) {
-        const int tile = blockIdx.x + lt * gridDim.x;
-        const int nt = tile % p.NTL;
-        const int b = tile / (p.NTL * p.MT);
+        const int tile = tile_of(lt);
+        int b, mt_, nt;
+        decode(tile, b, mt_, nt);
         const unsigned char* src = p.bops + (static_cast<size_t>(b) * p.NTL + nt) * p.NCB * (4 * static_cast<size_t>(b_arr));
         for (int cb = 0; cb < p.NCB; ++cb, ++it) {
           const int s = it % tc::STAGES;
@@ -390,9 +450,8 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     constexpr int kBiasRegs = 8;
     float bpart[kBiasRegs];
     auto bias_fetch = [&](int lt_) {
-      const int tile_ = blockIdx.x + lt_ * gridDim.x;
-      const int nt_ = tile_ % p.NTL;
-      const int b_ = tile_ / (p.NTL * p.MT);
+      int b_, mt__, nt_;
+      decode(tile_of(lt_), b_, mt__, nt_);
       const int e = (warp - tc::W_EPI0) * 32 + lane;
 #pragma unroll
       for (int sp = 0; sp < kBiasRegs; ++sp)
@@ -400,12 +459,11 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       for (int sp = kBiasRegs; sp < p.nsplit; ++sp)  // more than 8 channel blocks (C > 256): summed right away
         if (e < Nt) bpart[0] += p.bias[((static_cast<size_t>(sp) * p.B + b_) * p.NTL + nt_) * Nt + e];
     };
-    bias_fetch(0);
+    if (ntile_local > 0) bias_fetch(0);
     for (int lt = 0; lt < ntile_local; ++lt) {
-      const int tile = blockIdx.x + lt * gridDim.x;
-      const int nt = tile % p.NTL;
-      const int mt = (tile / p.NTL) % p.MT;
-      const int b = tile / (p.NTL * p.MT);
+      const int tile = tile_of(lt);
+      int b, mt, nt;
+      decode(tile, b, mt, nt);
       const int buf = lt & 1;
       const int n0 = nt * Nt;
       // bias of this tile's columns (sum of the prep kernel's per-channel-block partials): the partials were
@@ -433,8 +491,11 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       for (int h = 0; h < 2; ++h) {
         const int mrow = quarter * 32 + h * 16 + (lane >> 2);  // this lane's first frame; the second is +8
         const int tA = mt * tc::M + mrow, tB = tA + 8;
-        float* rowA = p.out + (static_cast<size_t>(b) * p.T_y + tA) * p.T_x + n0;
-        float* rowB = rowA + static_cast<size_t>(8) * p.T_x;
+        // streamed mode: row (mt % RT)*128 + mrow of utterance b's ring, every row and column of the tile is stored
+        const int ostride = p.stream ? p.pitch : p.T_x;
+        float* rowA = p.stream ? p.ring + (static_cast<size_t>(b) * p.RT * tc::M + static_cast<size_t>(mt % p.RT) * tc::M + mrow) * p.pitch + n0
+                               : p.out + (static_cast<size_t>(b) * p.T_y + tA) * p.T_x + n0;
+        float* rowB = rowA + static_cast<size_t>(8) * ostride;
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf) * 256u + (static_cast<uint32_t>(quarter * 32 + h * 16) << 16);
         // (+bias) and store one group of 16 columns held in registers
         auto emit = [&](int g, const uint32_t (&cur)[8]) {
@@ -446,7 +507,10 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
             const float2 oA = make_float2(__uint_as_float(cur[4 * i + 0]) + bq.x, __uint_as_float(cur[4 * i + 1]) + bq.y);
             const float2 oB = make_float2(__uint_as_float(cur[4 * i + 2]) + bq.x, __uint_as_float(cur[4 * i + 3]) + bq.y);
             const int n = n0 + c;
-            if (pair_ok && n + 1 < p.T_x) {
+            if (p.stream) {
+              *reinterpret_cast<float2*>(rowA + c) = oA;
+              *reinterpret_cast<float2*>(rowB + c) = oB;
+            } else if (pair_ok && n + 1 < p.T_x) {
               if (tA < p.T_y) *reinterpret_cast<float2*>(rowA + c) = oA;
               if (tB < p.T_y) *reinterpret_cast<float2*>(rowB + c) = oB;
             } else {
@@ -477,6 +541,16 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
       __syncwarp();
       if (warp == tc::W_EPI0 && lane == 0) trace_ev(p, tsm, tcnt, 2, 2, lt);
       if (lane == 0) ptx::mbar_arrive(&t_empty[buf]);
+      if (p.stream) {
+        // publish the tile: every epilogue warp's stores are ordered before the barrier, the fence makes them
+        // visible GPU-wide (cumulativity) before the count that the DP kernel's producer warps acquire
+        asm volatile("bar.sync 1, %0;" ::"n"(tc::N_EPI * 32) : "memory");
+        if (warp == tc::W_EPI0 && lane == 0) {
+          __threadfence();
+          atomicAdd(p.flags + static_cast<size_t>(b) * p.MT + mt, 1u);
+          if (p.tl) atomicMax(p.tl + 6, ptx_globaltimer());
+        }
+      }
     }
   } else if (warp >= tc::W_ZL0 && warp < tc::W_CV0) {
     // ---------------- z loaders: z_p (global, coalesced along frames) -> fp32 staging ring ----------------
@@ -496,14 +570,13 @@ __global__ void __launch_bounds__(tc::N_WARPS * 32, 1) neg_cent_tc_kernel(const 
     const float* ld_ptr = nullptr;
     int t_rem = 0;  // frames of this thread that exist (vec16: 0..4, else 0..1)
     auto ld_new_tile = [&]() {
-      const int tile = blockIdx.x + ld_lt * gridDim.x;
-      const int mt = (tile / p.NTL) % p.MT;
-      const int b = tile / (p.NTL * p.MT);
+      int b, mt, nt_;
+      decode(tile_of(ld_lt), b, mt, nt_);
       const int t = mt * tc::M + fm;
       t_rem = max(0, min(vec16 ? 4 : 1, p.T_y - t));
       ld_ptr = p.z_p + static_cast<size_t>(b) * p.C * p.T_y + (t_rem > 0 ? t : 0);
     };
-    ld_new_tile();
+    if (G > 0) ld_new_tile();
     for (int g = 0; g < G; ++g) {
       if (use >= 1) ptx::mbar_wait(&z_empty[zs], (use - 1) & 1);  // converters finished reading the slot
       float* dst = zstage + static_cast<size_t>(zs) * (tc::CB * tc::M) + fm;
@@ -644,15 +717,27 @@ static TcShape tc_shape(int B, int C, int T_y, int T_x) {
 
 size_t neg_cent_tc_scratch_bytes(int B, int C, int T_y, int T_x) { return tc_shape(B, C, T_y, T_x).total; }
 
+void neg_cent_tc_dims(int C, int T_y, int T_x, int* Nt, int* NTL, int* MT) {
+  const TcShape s = tc_shape(1, C, T_y, T_x);
+  *Nt = s.Nt;
+  *NTL = s.NTL;
+  *MT = s.MT;
+}
+
 int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
                 int B, int C, int T_y, int T_x, cudaStream_t st) {
+  return neg_cent_tc_impl(z_p, m_p, logs_p, out, scratch, scratch_bytes, B, C, T_y, T_x, st, nullptr);
+}
+
+int neg_cent_tc_impl(const float* z_p, const float* m_p, const float* logs_p, float* out, void* scratch, size_t scratch_bytes,
+                     int B, int C, int T_y, int T_x, cudaStream_t st, const TcStream* so) {
   const TcShape s = tc_shape(B, C, T_y, T_x);
   if (scratch_bytes < s.total || !scratch) return MAS_E_SCRATCH;
   if (reinterpret_cast<uintptr_t>(scratch) & 15u) return MAS_E_ALIGN;
   unsigned char* bops = static_cast<unsigned char*>(scratch);
   float* bias = reinterpret_cast<float*>(bops + ((s.bops_bytes + 255) & ~size_t(255)));
 
-  PrepParams pp{m_p, logs_p, bops, bias, B, C, T_x, s.Nt, s.NTL, s.NCB};
+  PrepParams pp{m_p, logs_p, bops, bias, B, C, T_x, s.Nt, s.NTL, s.NCB, so ? so->zero_base : nullptr, so ? so->zero_stride : 0};
   static const int g_dbg = getenv("MAS_NC_DEBUG") ? atoi(getenv("MAS_NC_DEBUG")) : 0;  // read once (benchmark bisection hook)
   if (!(g_dbg & 256)) neg_cent_prep_kernel<<<dim3(s.NTL * (s.Nt / 16), B, s.NPB), 64, 0, st>>>(pp);  // 4 chunks x 16 columns
   cudaError_t e = cudaGetLastError();
@@ -664,6 +749,17 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   tp.B = B; tp.C = C; tp.T_y = T_y; tp.T_x = T_x;
   tp.Nt = s.Nt; tp.NTL = s.NTL; tp.MT = s.MT; tp.NCB = s.NCB;
   tp.tiles = B * s.MT * s.NTL;
+  if (so) {
+    tp.stream = 1;
+    tp.ring = so->ring; tp.flags = so->flags; tp.t_ys = so->t_ys; tp.t_xs = so->t_xs;
+    tp.RT = so->RT; tp.pitch = so->pitch;
+    tp.tl = timeline_ptr();
+    const int grid = tp.tiles < so->grid ? tp.tiles : so->grid;
+    tp.n_long = so->n_long < grid ? so->n_long : grid;
+    tp.n1 = so->n1;
+    if (grid < 1 || tp.n_long < 1 || tp.n1 < 0 || tp.n1 + (tp.tiles + tp.n_long - 1) / tp.n_long > kMaxLocalTiles)
+      return MAS_E_UNSUPPORTED;
+  }
   tp.dbg = g_dbg;
   static unsigned long long* d_trace = nullptr;
   if (tp.dbg & 16) {
@@ -673,14 +769,16 @@ int neg_cent_tc(const float* z_p, const float* m_p, const float* logs_p, float* 
   }
   const size_t fixed = static_cast<size_t>(tc::STAGES) * (4 * tc::A_ARR + 4 * static_cast<size_t>(s.Nt) * (tc::CB / 8) * 16) + 512 + 2 * 256 * 4 + 128;
   tp.ZS = tc::ZS_MAX;
-  while (tp.ZS > 1 && fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE > 225 * 1024) --tp.ZS;
+  // dynamic + static (tile list, 3 KB) shared memory must stay within the 227 KB opt-in limit
+  while (tp.ZS > 1 && fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE > 221 * 1024) --tp.ZS;
   const size_t smem = fixed + static_cast<size_t>(tp.ZS) * tc::Z_STAGE + ((tp.dbg & 16) ? (4 * 200 * 16 + 64) : 0);
   static std::atomic<uint64_t> attr{0};
-  e = ensure_dyn_smem(neg_cent_tc_kernel, 227 * 1024, attr);
+  e = ensure_dyn_smem(neg_cent_tc_kernel, 223 * 1024, attr);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int sms = num_sms();
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tp.tiles < sms ? tp.tiles : sms);
+  const int want_ctas = so ? so->grid : sms;
+  cfg.gridDim = dim3(tp.tiles < want_ctas ? tp.tiles : want_ctas);
   cfg.blockDim = dim3(tc::N_WARPS * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

@@ -228,6 +228,8 @@ struct BsParams {
   unsigned char* path;      // [B][T_y][T_x] elements of es bytes, or nullptr
   const int32_t* fill_counters;  // [1] = zero-fill chunks finished
   int nchunks;
+  const uint32_t* fill_flag;     // streamed source: fill_flag[b * fill_stride] = 1 once utterance b's plane is zero-filled
+  int fill_stride;
   int T_y, T_x, TXP, G;
   int TXS;                  // shared-memory row stride in words (odd)
   int cols_per_warp;        // 32*K of the forward kernel: ceil(t_x / cols_per_warp) warps arrive per group
@@ -427,8 +429,10 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
   } else if (warp == 1 && p.path) {
     // the zero-fill must be complete before the ones are dropped
     if (lane == 0) {
-      while (ptx::ld_acquire_gpu_u32(reinterpret_cast<const uint32_t*>(p.fill_counters + 1)) <
-             static_cast<uint32_t>(p.nchunks)) {
+      const uint32_t* word = p.fill_flag ? p.fill_flag + static_cast<size_t>(b) * p.fill_stride
+                                         : reinterpret_cast<const uint32_t*>(p.fill_counters + 1);
+      const uint32_t need = p.fill_flag ? 1u : static_cast<uint32_t>(p.nchunks);
+      while (ptx::ld_acquire_gpu_u32(word) < need) {
         if (expired()) break;
         __nanosleep(100);
       }
@@ -600,6 +604,9 @@ struct DpConfig {
   DpSmem sm;
 };
 
+// Backtrack warps per CTA when the source is streamed: small batches leave SMs to spare (a CTA of 16 warps per
+// utterance, as in the ordinary mode); large ones pack four-warp CTAs onto a few SMs (fused_backtrack_sms).
+static int fused_bt_warps(int B) { return B <= 24 ? 16 : 4; }
 constexpr uint32_t kSmemMax = 227 * 1024;  // per CTA on sm_100
 constexpr uint32_t kSmemSM = 228 * 1024;   // per SM
 
@@ -618,7 +625,7 @@ static DpSmem dp_smem_layout(int K, int W, int nphys, int S, int BR) {
 // A superstep of a warp reads frames 32s-31*D .. 32s+31 (D = skew between lanes): Q+1 = ceil(31D/32)+1 chunks
 // are live and at least one more must be in flight, so the linear ring needs S >= Q+2 slots plus the mirror;
 // the select ring (D = 1, no mirror) needs 3.  D = 3 hides the SHFL latency completely, D = 1 not at all.
-static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg) {
+static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 208 * 1024) {
   int K = g_tune_wfK;
   if (K == 0) K = 2;  // K = 2 keeps the per-step dependency chain short and fills one scheduler per 64 columns
   if (K != 1 && K != 2 && K != 4) return false;
@@ -629,7 +636,7 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg) {
   }
   if (W > 8) return false;
   const int BR = 256;
-  const uint32_t budget = 208 * 1024;
+  if (budget < 48 * 1024) return false;
   const uint32_t slotset = static_cast<uint32_t>(W) * kRows * 32u * K * 4u;  // one chunk of every warp
   const int nphys = static_cast<int>((budget - 12 * 1024) / slotset);
   int linear = 1, skew = 0;
@@ -730,6 +737,30 @@ static unsigned long long one_bits(int dtype) {
   }
 }
 
+// where a CUDA call of the last failing entry point failed (diagnostics: mas_last_error_site)
+static thread_local int g_fail_line = 0;
+static int fail_at(cudaError_t e, int line) {
+  g_fail_line = line;
+  cudaGetLastError();  // a failed launch must not leak into the caller's next runtime call
+  return static_cast<int>(e);
+}
+int last_fail_line() { return g_fail_line; }
+
+// SMs to set aside for the streaming backtrack CTAs of a streamed (fused) call: they may share an SM neither with a
+// forward CTA nor with a contraction CTA, and all B of them should be resident while the DP runs.
+int fused_backtrack_sms(int B, int T_y, int T_x) {
+  const int TXS = T_x | 1, G = (T_y + 31) / 32;
+  const int warps = G + 1 < fused_bt_warps(B) ? (G + 1 < 2 ? 2 : G + 1) : fused_bt_warps(B);
+  size_t smem = (static_cast<size_t>(G) * TXS + static_cast<size_t>(warps) * TXS + G + 16) * 4;
+  if (smem > 200 * 1024) smem = (static_cast<size_t>(G) * TXS / 2 + 1 + static_cast<size_t>(warps) * TXS + G + 16) * 4;
+  int per_sm = static_cast<int>((kSmemSM - 1024) / (smem + 1024));  // 1 KB of system shared memory per resident CTA
+  const int by_threads = 2048 / (32 * warps), by_regs = 65536 / (64 * 32 * warps);
+  per_sm = per_sm < by_threads ? per_sm : by_threads;
+  per_sm = per_sm < by_regs ? per_sm : by_regs;
+  if (per_sm < 1) per_sm = 1;
+  return (B + per_sm - 1) / per_sm;
+}
+
 int num_sms() {
   static int sms[kMaxDevices] = {};
   const int dev = current_device();
@@ -743,7 +774,8 @@ int num_sms() {
 
 int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, const void* mask, int mask_dtype,
                  int64_t msb, int64_t msy, int64_t msx, void* path_out, int path_dtype, int32_t* index_out,
-                 void* scratch, size_t scratch_bytes, int B, int T_y, int T_x, cudaStream_t st) {
+                 void* scratch, size_t scratch_bytes, int B, int T_y, int T_x, cudaStream_t st, const FusedSrc* fused,
+                 bool probe_only) {
   if (B <= 0 || T_y <= 0 || T_x <= 0 || T_x > 2048 || T_y > (1 << 20)) return MAS_E_BAD_SHAPE;
   if (!neg_cent || !scratch) return MAS_E_NULL;
   if ((t_ys == nullptr) != (t_xs == nullptr)) return MAS_E_NULL;
@@ -770,6 +802,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   const int TXS = T_x | 1;  // odd shared-memory row stride
   const int G_ = (T_y + 31) / 32;
   int bt_warps = G_ + 1 < 16 ? (G_ + 1 < 2 ? 2 : G_ + 1) : 16;
+  // streamed source: the backtrack CTAs get a few SMs of their own (fused_backtrack_sms); small CTAs pack densely there,
+  // and four warps keep up with the DP (a group's walk takes ~1.5 us, the DP finishes a group per ~1 us)
+  if (fused && bt_warps > fused_bt_warps(B)) bt_warps = fused_bt_warps(B);
   size_t bs_smem = (static_cast<size_t>(G_) * TXS + static_cast<size_t>(bt_warps) * TXS + G_ + 16) * 4;
   int dec16 = 0;
   if (bs_smem > 200 * 1024) {  // long utterances: 16-bit exit columns instead of 32-bit decision words
@@ -781,7 +816,16 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   if ((mode == 2 || mode == 3) && !stream_ok) return MAS_E_UNSUPPORTED;
   // mode 3: streaming backtrack behind the WAVEFRONT forward kernel (mas_dp.cuh)
   DpConfig dc{};
+  // (Streamed source: a backtrack CTA sharing an SM with a forward CTA was measured to stretch the DP from 70 to 100 us
+  // at c2 -- its sixteen, even eight, polling and walking warps take the DP warps' issue slots -- so, exactly as in the
+  // ordinary mode, the forward CTAs fill their SM's shared memory and the backtrack CTAs run elsewhere.)
   const bool wf_ok = stream_ok && T_x <= 512 && pick_dp_config(T_y, T_x, &dc);
+  if (fused) {
+    if (!wf_ok || !dc.linear || dc.skew > 2 || !t_ys || !path_out || B + fused->reserve_ctas > g_num_sms ||
+        (fused->pitch & 3) || (reinterpret_cast<uintptr_t>(fused->ring) & 15u))
+      return MAS_E_UNSUPPORTED;
+    mode = 3;
+  }
   if (mode == 3 && !wf_ok) return MAS_E_UNSUPPORTED;
   if (mode < 0 && wf_ok && g_tune_wf != 0) mode = 3;
   FwdConfig fc{};
@@ -803,6 +847,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   int32_t* index = index_out ? index_out : reinterpret_cast<int32_t*>(sc + L.off_index);
   uint32_t* bits = reinterpret_cast<uint32_t*>(sc + L.off_bits);
 
+  if (probe_only) return MAS_OK;
   // K1: forward (+ backtrack when fused)
   cudaError_t e = cudaSuccess;
   if (wavefront) {
@@ -810,18 +855,32 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     dp.nc = neg_cent; dp.t_ys = t_ys; dp.t_xs = t_xs;
     dp.mask = mask; dp.mask_dtype = mask_dtype; dp.msb = msb; dp.msy = msy; dp.msx = msx;
     dp.lens = lens; dp.status = status; dp.mirror = mirror; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
-    dp.wo_counters = status + 4;
-    dp.pdl = g_tune_pdl == 2;  // see set_tuning: the forward kernel is an ordinary launch by default
+    dp.wo_counters = fused ? nullptr : status + 4;
+    dp.pdl = fused ? 1 : g_tune_pdl == 2;  // see set_tuning: the forward kernel is an ordinary launch by default
+    if (fused) {  // launched programmatically behind the contraction kernel and fed by it tile by tile
+      dp.tile_flags = fused->tile_flags; dp.tile_need = fused->tile_need; dp.RT = fused->RT; dp.MT = fused->MT;
+      dp.fill_out = static_cast<unsigned char*>(path_out);
+      dp.fill_bytes = static_cast<long long>(T_y) * T_x * es;
+      dp.fill_done = fused->fill_done; dp.fill_stride = fused->fill_stride;
+      // pace the fill so that it ends within ~60 % of the expected DP time (T_y x ~30 ns)
+      const double iters = static_cast<double>(dp.fill_bytes) / 2048.0;
+      const double ns = 0.6 * T_y * 30.0 / (iters > 1 ? iters : 1) - 20.0;
+      dp.fill_sleep = ns > 0 ? static_cast<int>(ns) : 0;
+    }
     dp.B = B; dp.T_y = T_y; dp.T_x = T_x;
     dp.S = dc.S; dp.W = dc.W; dp.TXP = TXP; dp.G = L.G; dp.BR = dc.BR;
     dp.sm = dc.sm;
     CUtensorMap tmap{};
     dp.use_tma = ((reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0) ? 1 : 0;
-    if (dp.use_tma && !make_tensor_map(&tmap, neg_cent, static_cast<long long>(B) * T_y, T_x, kRows, 32 * dc.K))
+    if (fused) {
+      dp.use_tma = 1;
+      if (!make_tensor_map(&tmap, fused->ring, static_cast<long long>(B) * fused->RT * 128, fused->pitch, kRows, 32 * dc.K))
+        return MAS_E_UNSUPPORTED;
+    } else if (dp.use_tma && !make_tensor_map(&tmap, neg_cent, static_cast<long long>(B) * T_y, T_x, kRows, 32 * dc.K))
       dp.use_tma = 0;
     if (!(g_debug_kernels & 8)) {  // (bit 3: watchdog test hook -- the backtrack kernel then never gets its words)
       e = launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
-      if (e != cudaSuccess) return static_cast<int>(e);
+      if (e != cudaSuccess) return fail_at(e, __LINE__);
       count_launch();
     }
   } else if (g_debug_kernels & 1) {
@@ -838,7 +897,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     fp.fused = fc.fused; fp.slot_bytes = fc.slot_bytes; fp.sm = fc.sm;
     const bool vec = (reinterpret_cast<uintptr_t>(neg_cent) & 15u) == 0 && (T_x % 4) == 0 && T_x >= fc.K;
     e = launch_fwd_dispatch(fc.K, vec, fp, fc.R, st);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     count_launch();
   }
 
@@ -856,18 +915,18 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     const size_t bt_smem = static_cast<size_t>(bp.GS) * bp.TXS * 6 + (bp.GS + 1) * 4 + static_cast<size_t>(bp.GS) * 32 * 4 + 64;
     static std::atomic<uint64_t> bt_attr{0};
     e = ensure_dyn_smem(mas_backtrack_kernel, 200 * 1024, bt_attr);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     long long tasks = static_cast<long long>(bp.GS) * T_x;
     int threads = tasks >= 1024 ? 1024 : static_cast<int>((tasks + 31) / 32 * 32);
     if (threads < 64) threads = 64;
     e = launch_pdl(mas_backtrack_kernel, dim3(B), dim3(threads), bt_smem, st, bp);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     count_launch();
   }
 
   // K3: dense path
   int nchunks = 0;
-  if (path_out && (g_debug_kernels & 4)) {
+  if (path_out && (g_debug_kernels & 4) && !fused) {
     WoParams wp{};
     wp.out = static_cast<unsigned char*>(path_out);
     wp.index = index;
@@ -893,9 +952,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     if (wo_smem < 0 || wo_smem > 56 * 1024) wo_smem = 0;  // forward CTA too small to exclude cheaply
     static std::atomic<uint64_t> wo_attr{0};
     e = ensure_dyn_smem(mas_writeout_kernel, 64 * 1024, wo_attr);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     e = launch_pdl(mas_writeout_kernel, dim3(grid), dim3(256), static_cast<size_t>(wo_smem), st, wp);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     count_launch();
   }
 
@@ -909,6 +968,10 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     sp.path = (path_out && (g_debug_kernels & 4)) ? static_cast<unsigned char*>(path_out) : nullptr;
     sp.fill_counters = reinterpret_cast<int32_t*>(sc + L.off_status) + 4;
     sp.nchunks = nchunks;
+    if (fused) {
+      sp.fill_flag = fused->fill_done;
+      sp.fill_stride = fused->fill_stride;
+    }
     sp.T_y = T_y; sp.T_x = T_x; sp.TXP = TXP; sp.G = L.G; sp.TXS = TXS;
     sp.cols_per_warp = cols_per_warp;
     sp.dec16 = dec16;
@@ -920,9 +983,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     const size_t smem = bs_smem > static_cast<size_t>(excl) ? bs_smem : static_cast<size_t>(excl);
     static std::atomic<uint64_t> bs_attr{0};
     e = ensure_dyn_smem(mas_backtrack_stream_kernel, 200 * 1024, bs_attr);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     e = launch_pdl(mas_backtrack_stream_kernel, dim3(B), dim3(32 * bt_warps), smem, st, sp);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (e != cudaSuccess) return fail_at(e, __LINE__);
     count_launch();
   }
   return MAS_OK;
@@ -935,6 +998,7 @@ size_t maximum_path_scratch_bytes(int B, int T_y, int T_x) {
 
 void set_debug_kernels(int mask) { g_debug_kernels = mask; }
 void set_timeline(unsigned long long* dev_ptr) { g_timeline = dev_ptr; }
+unsigned long long* timeline_ptr() { return g_timeline; }
 void set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
 // pdl: 0 = every kernel an ordinary launch; 1 (default) = write-out and backtrack kernels launched

@@ -187,7 +187,13 @@ def _run_host(neg_cent: torch.Tensor, t_ys: torch.Tensor, t_xs: torch.Tensor, ch
     t_xs = t_xs.to(torch.int32).contiguous()
     # the path leaves the device already in neg_cent's dtype (no int32 -> float pass on the host, __init__.py:20), and
     # the entry zeroes the padded rows it does not copy (no np.zeros pass, __init__.py:15)
-    paths = torch.empty((B, T_y, T_x), dtype=neg_cent.dtype)
+    # Page-locked result (torch's caching host allocator: the cudaHostAlloc is paid once, later calls reuse the block):
+    # the device writes it at link speed with no staging copy and no first-touch page faults; to the caller it is an
+    # ordinary CPU tensor.
+    try:
+        paths = torch.empty((B, T_y, T_x), dtype=neg_cent.dtype, pin_memory=True)
+    except RuntimeError:   # no usable CUDA driver: the C entry below reports that (there is no CPU implementation)
+        paths = torch.empty((B, T_y, T_x), dtype=neg_cent.dtype)
     rc = L.mas_maximum_path_host(paths.data_ptr(), _DT[neg_cent.dtype], 1, values.data_ptr(), t_ys.data_ptr(),
                                  t_xs.data_ptr(), B, T_y, T_x)
     if rc > 0 and (rc & 0xFF) == 0:
