@@ -579,18 +579,23 @@ def run_ours(args, rank, world, local_rank):
             duplex_s = (time.perf_counter() - t1) / 5
             h_vals[1].copy_(ncs[1 % len(ncs)])
             link = {"h2d_gbs": gbs[0], "d2h_gbs": gbs[1], "duplex_gbs": 2 * plane_bytes / duplex_s / 1e9,
+                    "h2d_bound": B / (valid_row_bytes / (gbs[0] * 1e9)),
                     "duplex_bound": B / (duplex_s * valid_row_bytes / plane_bytes),
-                    "note": "pinned cudaMemcpy of one whole plane each way, alone and then both at once; duplex_bound = "
-                            "alignments/s if a step cost exactly its two copies at the both-at-once rate"}
+                    "note": "pinned cudaMemcpy of one whole plane each way, alone and then both at once; h2d_bound = "
+                            "alignments/s if a step cost exactly its inbound copy (what the entry moves now: the path "
+                            "comes back as the 4-byte-per-frame index and is materialised by host threads); duplex_bound "
+                            "= the same if the dense path crossed the link too (round 1's pipeline, MAS_HOST_DENSE=1)"}
             del d_tmp, d_tmp2
         if rank == 0:
             from oracle import mas_oracle
             want = mas_oracle.maximum_path_numpy(h_vals[0].numpy(), t_ys, t_xs)
             assert np.array_equal(h_paths[0].numpy(), want), "e2e path differs from the oracle"
         e2e = {"value": world * B * e2e_steps / float(td.item()), "unit": UNIT,
-               "h2d_bytes_per_step": valid_row_bytes + 8 * B, "d2h_bytes_per_step": valid_row_bytes + 64,
-               "copied": "leading rows of every utterance up to the longest of its group, both directions (the "
-                         "padded tail is never needed, as in core.pyx:13-33); host paths buffer zero-filled once",
+               "h2d_bytes_per_step": valid_row_bytes + 8 * B, "d2h_bytes_per_step": 4 * B * T_y + 64,
+               "copied": "in: leading rows of every utterance's neg_cent up to the longest of its group (the padded tail "
+                         "is never needed, as in core.pyx:13-33); out: the int32 per-frame index [B,T_y] -- the dense int32 "
+                         "path (one 1 per frame) is written into the caller's buffer by the entry's host threads, rows "
+                         "below t_y in full (zeros and the one); host paths buffer zero-filled once by the caller",
                "pcie_link": link, "pcie_all_ranks_duplex": all_ranks_duplex,
                "rank_seconds": {"min": float(tmin.item()), "max": float(td.item())},
                "steps": e2e_steps, "timer": "host wall clock around the synchronous C call, max over ranks",
@@ -839,7 +844,7 @@ def main():
                          "the drop-in (bench_c5.py)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's B per GPU; strong: the workload's B is the global batch, split over the GPUs")
-    ap.add_argument("--c5-batch", type=int, default=32, help="utterances per GPU in the c5 training step")
+    ap.add_argument("--c5-batch", type=int, default=64, help="utterances per GPU in the c5 training step")
     ap.add_argument("--full-length", action="store_true",
                     help="headline on the full-length variant (default: variable lengths, BASELINE.json configs[1])")
     ap.add_argument("--no-graph", action="store_true")

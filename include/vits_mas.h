@@ -107,8 +107,10 @@ int mas_maximum_path(const float* neg_cent,
  * over the first t_ys[b] rows of a caller-zeroed `paths` (core.pyx:13-33, __init__.py:15), rows
  * y >= t_ys[b] need not be read from `values` nor written to `paths` (the padded tail is skipped up to
  * the longest utterance of each internal group; what is written there is zeros): pass `paths`
- * zero-filled, as np.zeros does.  Rows below t_ys[b] are written in full (zeros and ones).  Uses internal streams and
- * cached device/pinned buffers; not re-entrant (the reference has a single caller thread).
+ * zero-filled, as np.zeros does.  Rows below t_ys[b] are written in full (zeros and ones).  Only `values` crosses the
+ * link in full: the path comes back as the 4-byte-per-frame index and is written into `paths` by a small pool of host
+ * threads of the library's own (MAS_HOST_THREADS, default min(8, cores/2)) while later groups are still in flight.
+ * Uses internal streams and cached device/pinned buffers; not re-entrant (the reference has a single caller thread).
  * Returns 0, a MAS_E_* code, or MAS_STATUS_* bits << 8 when an utterance had invalid lengths.
  */
 int mas_maximum_path_c_host(int32_t* paths, const float* values, const int32_t* t_ys, const int32_t* t_xs,

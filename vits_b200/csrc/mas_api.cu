@@ -1,7 +1,10 @@
 // mas_api.cu -- the extern "C" surface declared in include/vits_mas.h, plus the host-buffer
 // entry that mirrors the reference's native call maximum_path_c (monotonic_align/core.pyx:38).
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
 #include <cstdint>
 #include <cstring>
 #include <cstdlib>
@@ -55,9 +58,12 @@ struct HostCtx {
   cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr, nullptr};
   void* d_values = nullptr;
   void* d_paths = nullptr;
+  void* d_index = nullptr;      // [B][T_y] int32 per-frame text position (index-only pipeline)
+  int32_t* h_index = nullptr;   // pinned host copy of it
+  size_t cap_index = 0;
   void* d_lens = nullptr;
   void* d_scratch = nullptr;
-  cudaEvent_t ev_in[kChunks] = {}, ev_k[kChunks] = {};  // group c: inputs landed / kernels done
+  cudaEvent_t ev_in[kChunks] = {}, ev_k[kChunks] = {}, ev_idx[kChunks] = {};  // group c: inputs landed / kernels done / index on the host
   int32_t* h_status = nullptr;  // pinned, kChunks words
   size_t cap_cells = 0, cap_path_bytes = 0, cap_lens = 0, cap_scratch = 0;
   bool ready = false;
@@ -68,6 +74,8 @@ HostCtx g_hosts[mas::kMaxDevices];
 void host_release() {
   if (g_host.d_values) cudaFree(g_host.d_values);
   if (g_host.d_paths) cudaFree(g_host.d_paths);
+  if (g_host.d_index) cudaFree(g_host.d_index);
+  if (g_host.h_index) cudaFreeHost(g_host.h_index);
   if (g_host.d_lens) cudaFree(g_host.d_lens);
   if (g_host.d_scratch) cudaFree(g_host.d_scratch);
   if (g_host.h_status) cudaFreeHost(g_host.h_status);
@@ -76,6 +84,8 @@ void host_release() {
   for (auto& e : g_host.ev_in)
     if (e) cudaEventDestroy(e);
   for (auto& e : g_host.ev_k)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : g_host.ev_idx)
     if (e) cudaEventDestroy(e);
   g_host = HostCtx{};
 }
@@ -86,11 +96,12 @@ void host_release() {
     if (e_ != cudaSuccess) return static_cast<int>(e_); \
   } while (0)
 
-int host_prepare(size_t cells, size_t lens, size_t scratch, int path_es) {
+int host_prepare(size_t cells, size_t lens, size_t scratch, int path_es, size_t index_words) {
   if (!g_host.ready) {
     for (auto& s : g_host.streams) MAS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto& e : g_host.ev_in) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : g_host.ev_k) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_host.ev_idx) MAS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     MAS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_host.h_status), HostCtx::kChunks * sizeof(int32_t),
                            cudaHostAllocDefault));
     g_host.ready = true;
@@ -101,6 +112,16 @@ int host_prepare(size_t cells, size_t lens, size_t scratch, int path_es) {
     g_host.cap_cells = 0;
     MAS_CUDA(cudaMalloc(&g_host.d_values, cells * 4));
     g_host.cap_cells = cells;
+  }
+  if (index_words > g_host.cap_index) {
+    if (g_host.d_index) cudaFree(g_host.d_index);
+    if (g_host.h_index) cudaFreeHost(g_host.h_index);
+    g_host.d_index = nullptr;
+    g_host.h_index = nullptr;
+    g_host.cap_index = 0;
+    MAS_CUDA(cudaMalloc(&g_host.d_index, index_words * sizeof(int32_t)));
+    MAS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_host.h_index), index_words * sizeof(int32_t), cudaHostAllocDefault));
+    g_host.cap_index = index_words;
   }
   if (cells * path_es > g_host.cap_path_bytes) {
     if (g_host.d_paths) cudaFree(g_host.d_paths);
@@ -201,6 +222,141 @@ int mas_maximum_path_host(void* paths, int path_dtype, int zero_tail, const floa
   return host_run(paths, path_dtype, zero_tail, values, t_ys, t_xs, B, T_y, T_x);
 }
 
+// ---- host-side materialisation of the dense path from the per-frame index -------------------------------------
+// The dense [B,T_y,T_x] path is one 1 per frame: 4 bytes of information per T_x*4 bytes of tensor.  The host entry
+// therefore brings back only the int32 index (0.26 MB at c2 instead of 42.5 MB) and writes the rows -- zeros and the
+// one -- into the caller's buffer with a small pool of host threads while the next groups' inputs are still crossing
+// the link: PCIe then carries the input only (the link, not the GPU, bounds this entry).
+namespace {
+struct ExpandJob {
+  unsigned char* paths;    // caller's buffer
+  const int32_t* index;    // pinned host copy of the device index, [B][T_y]
+  const int32_t* t_ys;
+  const int32_t* t_xs;
+  int T_y, T_x, es, zero_tail;
+  unsigned long long one;
+};
+
+void expand_utterance(const ExpandJob& j, int b) {
+  const size_t plane = static_cast<size_t>(j.T_y) * j.T_x * j.es;
+  unsigned char* pb = j.paths + plane * b;
+  const int ty = j.t_ys[b], tx = j.t_xs[b];
+  const bool valid = ty >= 1 && tx >= 1 && ty <= j.T_y && tx <= j.T_x && tx <= ty;  // as the kernels decide (mas_dp.cuh)
+  const int rows = ty < 0 ? 0 : (ty > j.T_y ? j.T_y : ty);
+  // rows below t_y are written in full; rows at or beyond it stay as the caller zeroed them (core.pyx never touches
+  // them), unless the caller asked for them to be zeroed here
+  memset(pb, 0, j.zero_tail ? plane : static_cast<size_t>(rows) * j.T_x * j.es);
+  if (!valid) return;
+  const int32_t* idx = j.index + static_cast<size_t>(b) * j.T_y;
+  for (int y = 0; y < rows; ++y) {
+    const int x = idx[y];
+    if (x < 0 || x >= j.T_x) continue;
+    unsigned char* cell = pb + (static_cast<size_t>(y) * j.T_x + x) * j.es;
+    switch (j.es) {
+      case 1: *cell = static_cast<unsigned char>(j.one); break;
+      case 2: *reinterpret_cast<uint16_t*>(cell) = static_cast<uint16_t>(j.one); break;
+      case 4: *reinterpret_cast<uint32_t*>(cell) = static_cast<uint32_t>(j.one); break;
+      default: *reinterpret_cast<unsigned long long*>(cell) = j.one; break;
+    }
+  }
+}
+
+// Persistent worker pool (created on first use; the calling thread works too).  Tasks are utterances.
+class ExpandPool {
+ public:
+  static ExpandPool& get() {
+    static ExpandPool pool;
+    return pool;
+  }
+  int threads() const { return static_cast<int>(workers_.size()) + 1; }
+  void begin(const ExpandJob& job) {
+    std::lock_guard<std::mutex> lk(m_);
+    job_ = job;
+    pending_.clear();
+    head_ = 0;
+    outstanding_ = 0;
+  }
+  void add(int b0, int nb) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      for (int b = b0; b < b0 + nb; ++b) pending_.push_back(b);
+      outstanding_ += nb;
+    }
+    cv_.notify_all();
+  }
+  void finish() {  // the caller helps, then waits for the stragglers
+    for (;;) {
+      int b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        if (head_ < pending_.size()) b = pending_[head_++];
+        else {
+          done_cv_.wait(lk, [&] { return outstanding_ == 0; });
+          return;
+        }
+      }
+      expand_utterance(job_, b);
+      complete_one();
+    }
+  }
+
+ private:
+  ExpandPool() {
+    int n = 0;
+    if (const char* e = getenv("MAS_HOST_THREADS")) n = atoi(e);
+    if (n <= 0) {
+      const unsigned hw = std::thread::hardware_concurrency();
+      n = hw >= 16 ? 8 : (hw >= 4 ? static_cast<int>(hw) / 2 : 1);
+    }
+    if (n > 32) n = 32;
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~ExpandPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void complete_one() {
+    std::lock_guard<std::mutex> lk(m_);
+    if (--outstanding_ == 0) done_cv_.notify_all();
+  }
+  void loop() {
+    for (;;) {
+      int b;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || head_ < pending_.size(); });
+        if (stop_) return;
+        b = pending_[head_++];
+      }
+      expand_utterance(job_, b);
+      complete_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<int> pending_;
+  size_t head_ = 0;
+  int outstanding_ = 0;
+  bool stop_ = false;
+  ExpandJob job_{};
+};
+
+unsigned long long one_pattern(int dtype) {
+  switch (dtype) {
+    case MAS_F32: return 0x3F800000ull;
+    case MAS_F16: return 0x3C00ull;
+    case MAS_BF16: return 0x3F80ull;
+    case MAS_F64: return 0x3FF0000000000000ull;
+    default: return 1ull;
+  }
+}
+}  // namespace
+
 static int host_run(void* paths, int path_dtype, int zero_tail, const float* values, const int32_t* t_ys,
                     const int32_t* t_xs, int B, int T_y, int T_x) {
   if (B <= 0 || T_y <= 0 || T_x <= 0) return MAS_E_BAD_SHAPE;
@@ -208,14 +364,15 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
   const int es = path_elem_size(path_dtype);
   if (es == 0) return MAS_E_BAD_DTYPE;
   const size_t plane = static_cast<size_t>(T_y) * T_x;
-  // Groups of about 12 MB: enough of them to overlap the two copy directions and the kernels, few enough
-  // that the ~11 driver calls per group stay off the critical path (c2, 2 x 50 MB: 4 groups 46.4k
-  // alignments/s full-length, 8 groups 44.5k, 16 groups 38.3k; the duplex link bound is 59.5k).
+  // Groups of about 12 MB: enough of them to overlap the copies, the kernels and the host-side materialisation, few
+  // enough that the ~10 driver calls per group stay off the critical path.
   static const int forced_groups = [] {
     const char* e = getenv("MAS_HOST_GROUPS");  // tuning hook
     const int v = e ? atoi(e) : 0;
     return v > 0 && v <= HostCtx::kChunks - 2 ? v : 0;
   }();
+  // MAS_HOST_DENSE=1: the round-1 pipeline (the dense path crosses the link too) -- kept for A/B measurements
+  static const bool dense_d2h = getenv("MAS_HOST_DENSE") && atoi(getenv("MAS_HOST_DENSE")) != 0;
   int want_chunks = forced_groups;
   if (!want_chunks) {
     const size_t total = plane * B * 4, target = size_t(12) << 20;
@@ -224,8 +381,8 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
   }
   const int nch = B < want_chunks ? B : want_chunks;
   const int per = (B + nch - 1) / nch;
-  // Tapered groups: the first inbound and the last outbound copy run with the other direction idle, so the
-  // first and last group are a quarter of the nominal size (c2: 4, 12, 16, 16, 12, 4 utterances).
+  // Tapered groups: nothing overlaps the first group's inbound copy nor the last group's kernels and
+  // materialisation, so the first and last group are a quarter of the nominal size (c2: 4, 12, 16, 16, 12, 4).
   int gsize[HostCtx::kChunks];
   int ng = 0;
   {
@@ -249,22 +406,26 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
   }
   const size_t sc_one = (mas::maximum_path_scratch_bytes(per, T_y, T_x) + 255) & ~size_t(255);
   if (sc_one == 0) return MAS_E_BAD_SHAPE;
-  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * ng, es);
+  int rc = host_prepare(plane * B, static_cast<size_t>(B), sc_one * ng, dense_d2h ? es : 0,
+                        dense_d2h ? 0 : static_cast<size_t>(B) * T_y);
   if (rc != MAS_OK) return rc;
 
   float* d_values = static_cast<float*>(g_host.d_values);
   unsigned char* d_paths = static_cast<unsigned char*>(g_host.d_paths);
+  int32_t* d_index = static_cast<int32_t*>(g_host.d_index);
+  int32_t* h_index = g_host.h_index;
   int32_t* d_ty = static_cast<int32_t*>(g_host.d_lens);
   int32_t* d_tx = d_ty + B;
-  // One stream feeds the inputs group by group without ever waiting for anything (H2D copy engine busy
-  // from the first byte to the last), two streams run the kernels of alternate groups, one stream returns
-  // the paths (D2H copy engine); events hand each group from stage to stage.  (With whole groups
-  // round-robined over four streams, a stream's next H2D queued behind its previous D2H and the inbound
-  // engine idled: 1.41 ms per c2 call for 2 x 50 MB.)
+  // One stream feeds the inputs group by group without ever waiting for anything (H2D copy engine busy from the
+  // first byte to the last), two streams run the kernels of alternate groups, one stream returns the results (D2H
+  // copy engine); events hand each group from stage to stage.
   cudaStream_t s_in = g_host.streams[0], s_out = g_host.streams[3];
   MAS_CUDA(cudaMemcpyAsync(d_ty, t_ys, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
   MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
   MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * ng, s_in));
+  ExpandPool* pool = dense_d2h ? nullptr : &ExpandPool::get();
+  if (pool) pool->begin(ExpandJob{static_cast<unsigned char*>(paths), h_index, t_ys, t_xs, T_y, T_x, es, zero_tail,
+                                  one_pattern(path_dtype)});
   int nused = 0;
   for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
     const int nb = gsize[c];
@@ -273,18 +434,29 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
     MAS_CUDA(copy_leading_rows(d_values, values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
     MAS_CUDA(cudaEventRecord(g_host.ev_in[c], s_in));
     MAS_CUDA(cudaStreamWaitEvent(s_k, g_host.ev_in[c], 0));
-    rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0 * es,
-                           path_dtype, nullptr, sc, sc_one, nb, T_y, T_x, s_k);
+    if (dense_d2h)
+      rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, d_paths + plane * b0 * es,
+                             path_dtype, nullptr, sc, sc_one, nb, T_y, T_x, s_k);
+    else  // index only: no dense path is written on the device at all
+      rc = mas::maximum_path(d_values + plane * b0, d_ty + b0, d_tx + b0, nullptr, 0, 0, 0, 0, nullptr, MAS_I32,
+                             d_index + static_cast<size_t>(b0) * T_y, sc, sc_one, nb, T_y, T_x, s_k);
     if (rc != MAS_OK) {
       for (auto& s : g_host.streams) cudaStreamSynchronize(s);
+      if (pool) pool->finish();
       return rc;
     }
     MAS_CUDA(cudaEventRecord(g_host.ev_k[c], s_k));
     MAS_CUDA(cudaStreamWaitEvent(s_out, g_host.ev_k[c], 0));
-    MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out, es));
+    if (dense_d2h) {
+      MAS_CUDA(copy_leading_rows(paths, d_paths, t_ys, b0, nb, T_y, T_x, cudaMemcpyDeviceToHost, s_out, es));
+    } else {
+      MAS_CUDA(cudaMemcpyAsync(h_index + static_cast<size_t>(b0) * T_y, d_index + static_cast<size_t>(b0) * T_y,
+                               static_cast<size_t>(nb) * T_y * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+      MAS_CUDA(cudaEventRecord(g_host.ev_idx[c], s_out));
+    }
     nused = c + 1;
   }
-  if (zero_tail) {
+  if (dense_d2h && zero_tail) {
     // the rows no copy writes (at or beyond the longest utterance of each group), zeroed on the host while the
     // copies are in flight: the caller may then hand in an uninitialised buffer (no np.zeros pass of its own)
     for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
@@ -301,6 +473,17 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
   MAS_CUDA(cudaMemcpy2DAsync(g_host.h_status, sizeof(int32_t),
                              static_cast<unsigned char*>(g_host.d_scratch) + mas_scratch_status_offset(), sc_one,
                              sizeof(int32_t), nused, cudaMemcpyDeviceToHost, s_out));
+  if (pool) {
+    // hand each group to the pool as soon as its index has landed, work on it too, and wait for the last row
+    cudaError_t ee = cudaSuccess;
+    for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
+      const cudaError_t e1 = cudaEventSynchronize(g_host.ev_idx[c]);
+      if (e1 != cudaSuccess) ee = e1;
+      pool->add(b0, gsize[c]);
+    }
+    pool->finish();
+    if (ee != cudaSuccess) return static_cast<int>(ee);
+  }
   for (auto& s : g_host.streams) MAS_CUDA(cudaStreamSynchronize(s));
   int status = 0;
   for (int c = 0; c < nused; ++c) status |= g_host.h_status[c];
