@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OBJ = os.path.join(_HERE, "build")
 LIB_PATH = os.path.join(_HERE, "libvits_mas.so")
-SOURCES = ["mas_path.cu", "mas_fwd_k1.cu", "mas_fwd_k2.cu", "mas_fwd_k3.cu", "mas_fwd_k4.cu", "mas_fwd_k6.cu", "mas_fwd_k8.cu", "mas_dp_k1.cu", "mas_dp_k2.cu", "mas_dp_k4.cu", "mas_neg_cent.cu",
+SOURCES = ["mas_path.cu", "mas_fwd_k1.cu", "mas_fwd_k2.cu", "mas_fwd_k3.cu", "mas_fwd_k4.cu", "mas_fwd_k6.cu", "mas_fwd_k8.cu", "mas_dp_k1.cu", "mas_dp_k2.cu", "mas_dp_k4.cu", "mas_dp2_k2.cu", "mas_neg_cent.cu",
            "mas_neg_cent_tc.cu", "mas_fused.cu", "mas_consumers.cu", "mas_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

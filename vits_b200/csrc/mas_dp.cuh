@@ -71,6 +71,7 @@ struct DpParams {
   uint32_t* fill_done;         // [B] (stride fill_stride words), set to 1 after the fence
   int fill_stride;
   int fill_sleep;              // ns between bursts of four 512-byte store instructions
+  int warm;                    // mas_dp2_kernel: 1 = an idle warp pre-executes the plain superstep variant (instruction cache)
   DpSmem sm;
 };
 

@@ -36,6 +36,7 @@
 
 #include "mas_forward.cuh"
 #include "mas_dp.cuh"
+#include "mas_dp2.cuh"
 
 namespace mas {
 
@@ -599,6 +600,10 @@ static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int 
   }
 }
 
+constexpr int kDp2Default = 33;  // mas_set_tuning3 `wavefront` value used when it is -1: mas_dp2 with the warmer
+// the second-generation wavefront kernel covers K = 2 (every automatic choice) unless the first one is asked for
+static bool dp2_selected(int K) { return K == 2 && g_tune_wf != 1 && ((g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & ~1) == 32; }
+
 struct DpConfig {
   int K, W, S, BR, linear, skew;
   DpSmem sm;
@@ -646,7 +651,8 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 20
   // T_x = 192) 39.7 / 38.1 / 44.2 us per call at skew 1 / 2 / 3 with variable lengths (40.3 / 39.7 / 46.3
   // full-length); four DP warps (c3, T_x = 256) 53.8 / 55.2 / 69.7 us.  A larger skew takes more of the
   // neighbour's SHFL latency off the chain but adds a superstep of lag per warp hop.
-  else if (nphys >= 5 && W <= 3) skew = 2;
+  // (the second-generation kernel, mas_dp2.cuh: 30.4 / 31.0 us at skew 1 / 2 on c2, equal on c3 -- skew 1)
+  else if (nphys >= 5 && W <= 3 && !dp2_selected(K)) skew = 2;
   else if (nphys >= 4) skew = 1;
   else { linear = 0; skew = 1; }
   const int Q = (31 * skew + 31) / 32;
@@ -878,8 +884,17 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
         return MAS_E_UNSUPPORTED;
     } else if (dp.use_tma && !make_tensor_map(&tmap, neg_cent, static_cast<long long>(B) * T_y, T_x, kRows, 32 * dc.K))
       dp.use_tma = 0;
+    // Second-generation kernel (mas_dp2.cuh): linear ring, K = 2, skew <= 2, ordinary source.  mas_set_tuning3's
+    // `wavefront`: -1 automatic, 1 the first-generation kernel, 32 = mas_dp2, 33 = mas_dp2 with the instruction-cache
+    // warmer.
+    int dp2_hs = 0;
+    if (!fused && dc.linear && dc.skew <= 2 && dp2_selected(dc.K)) {
+      dp2_hs = 32;
+      dp.warm = (g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & 1;
+    }
     if (!(g_debug_kernels & 8)) {  // (bit 3: watchdog test hook -- the backtrack kernel then never gets its words)
-      e = launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
+      e = dp2_hs ? launch_dp2_k2(tmap, dp, dc.skew, st)
+                 : launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
       if (e != cudaSuccess) return fail_at(e, __LINE__);
       count_launch();
     }
