@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   const int S = p.S, W = p.W, BR = p.BR;
   const int nphys = S + 1;
   // the instruction-cache warmer: an idle warp on the scheduler of the last DP warp (which starts last)
-  const bool shadow = p.warm != 0 && spread && wid == (W < 3 ? 4 + W : 6);
+  const bool shadow = (p.warm & 1) != 0 && spread && wid == (W < 3 ? 4 + W : 6);
   const int dwa = shadow ? 0 : dw;  // whose ring / barriers a warp addresses
 
   unsigned char* ring_all = smem + p.sm.ring;
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   // otherwise idle warps of the CTA help with the strided walk over column 0 -- 1024 sectors per utterance, one DRAM
   // round trip when every thread issues a handful of loads instead of two batches of sixteen by one warp.
   const bool lenw = dw == W + NP;
-  const bool helper = spread && dw < 0 && !shadow && p.t_ys == nullptr;
+  const bool dummy_walk = (p.warm & 4) != 0 && p.t_ys != nullptr && p.mask != nullptr;  // (experiment: the walk's traffic alone)
+  const bool helper = spread && dw < 0 && !shadow && (p.t_ys == nullptr || dummy_walk);
   if (dw < 0 && !shadow && !helper) return;  // filler warps
   if (lenw || helper) {
     if (lenw && lane == 0) {
@@ -146,14 +147,14 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
       ptx::pdl_launch_dependents();
     }
     int t_y, t_x;
-    if (p.t_ys != nullptr) {
+    if (p.t_ys != nullptr && !(dummy_walk && !lenw)) {
       t_y = p.t_ys[b];
       t_x = p.t_xs[b];
     } else {
       int nh = 0, rank = 0;  // warps that walk the mask, and this warp's place among them
       if (spread) {
         for (int u = 0; u < 12; ++u) {
-          const bool sh = p.warm != 0 && u == (W < 3 ? 4 + W : 6);
+          const bool sh = (p.warm & 1) != 0 && u == (W < 3 ? 4 + W : 6);
           const bool part = u == 11 || (!sh && ((u < 3 && u >= W) || (u > 3 && (u & 3) != 3)));
           nh += part ? 1 : 0;
           rank += part && u < wid ? 1 : 0;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
         if (!lenw) return;
         if (lane == 0)
           while (ptx::ld_volatile_s32(&lens_s[3]) < nh) {
+            __nanosleep(200);
           }
         __syncwarp();
         sy = *reinterpret_cast<volatile double*>(&red[0]);

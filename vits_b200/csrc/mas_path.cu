@@ -236,6 +236,8 @@ struct BsParams {
   int cols_per_warp;        // 32*K of the forward kernel: ceil(t_x / cols_per_warp) warps arrive per group
   int32_t* status;          // sticky MAS_STATUS_* bits (MAS_STATUS_TIMEOUT: a poll below gave up)
   int32_t* mirror;          // host-mapped copy of the status bits (one word per bit) or nullptr
+  int lazy;                 // 1: the group walks do not wait for the lengths (wavefront forward kernels: every column of every
+                            // group gets its tagged word whatever the lengths are)
   int dec16;                // 1: tables hold 16-bit exit columns (long utterances), the per-frame index is re-walked from the words
   int es;
   unsigned long long one;
@@ -313,20 +315,43 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     *dead = 1;
     return true;
   };
-  if (tid == 0) {
-    uint2 lt;
-    while ((lt = load_tagged(p.lenstag + b)).y != 1u) {
-      if (expired()) {
-        lt = make_uint2(0u, 1u);
-        break;
+  // The lengths.  Eager form: wait for them, then start on the groups.  Lazy form (wavefront forward kernels): the group
+  // walks need neither -- every column of every group arrives tagged, and an entry column's walk only ever moves left, so
+  // walking all T_x entry columns gives the same exits for the real ones -- and t_y only says which group is the top one.
+  // With the lengths taken from the mask they arrive ~10 us into a c2 call: the eager form then started 5 us late and did
+  // not catch up before the end of the call (tools/mask_traffic.py: 1.4 us per call).
+  int t_y = -1, t_x = p.T_x;
+  bool known = false;
+  if (!p.lazy) {
+    if (tid == 0) {
+      uint2 lt;
+      while ((lt = load_tagged(p.lenstag + b)).y != 1u) {
+        if (expired()) {
+          lt = make_uint2(0u, 1u);
+          break;
+        }
+        __nanosleep(100);
       }
-      __nanosleep(100);
+      smisc[0] = static_cast<int>(lt.x >> 12);
+      smisc[1] = static_cast<int>(lt.x & 4095u);
     }
-    smisc[0] = static_cast<int>(lt.x >> 12);
-    smisc[1] = static_cast<int>(lt.x & 4095u);
+    __syncthreads();
+    t_y = smisc[0];
+    t_x = smisc[1];
+    known = true;
   }
-  __syncthreads();
-  const int t_y = smisc[0], t_x = smisc[1];
+  auto poll_lens = [&]() {  // (warp-uniform)
+    if (known) return;
+    uint2 lt = make_uint2(0u, 0u);
+    if (lane == 0) lt = load_tagged(p.lenstag + b);
+    lt.x = __shfl_sync(0xffffffffu, lt.x, 0);
+    lt.y = __shfl_sync(0xffffffffu, lt.y, 0);
+    if (lt.y == 1u) {
+      known = true;
+      t_y = static_cast<int>(lt.x >> 12);
+      t_x = static_cast<int>(lt.x & 4095u);
+    }
+  };
   constexpr uint32_t tag = 1u;  // cleared by the forward kernel before this kernel can start
   auto finish = [&]() {
     // This kernel is the last of the call's chain and the next call's forward kernel waits only for it:
@@ -335,81 +360,97 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     ptx::pdl_wait();
   };
   int32_t* idx_b = p.index ? p.index + static_cast<size_t>(b) * p.T_y : nullptr;
-  if (t_y <= 0) {  // invalid lengths: the path stays all-zero
+  const uint2* bits_b = p.bits + static_cast<size_t>(b) * p.G * p.TXP;
+  uint32_t* stage = sstage + static_cast<size_t>(warp) * p.TXS;
+
+  // ---- groups below the top one: as soon as a group's words have arrived, walk it from every entry column ----
+  for (int g = warp; g < p.G; g += nw) {
+    const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
+    bool have = false;
+    for (;;) {
+      poll_lens();
+      if (known && (t_y <= 0 || g >= ((t_y - 1) >> 5))) break;  // the top group (handled below), or beyond it
+      // wait for the group's words: an element is valid once it carries this call's tag.  Poll ONE element per
+      // forward warp (the last column it owns, or the last valid column) with back-off -- 1000 warps re-reading
+      // whole rows would saturate the L2 -- then read the row and check every tag.
+      const int nfw = (t_x + p.cols_per_warp - 1) / p.cols_per_warp;  // forward warps that write the words walked here
+      bool ok = true;
+      if (lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
+      if (__all_sync(0xffffffffu, ok)) {
+        for (int x = lane; x < t_x; x += 32) {
+          const uint2 el = load_tagged(row + x);
+          stage[x] = el.x;
+          ok = ok && el.y == tag;
+        }
+        if (__all_sync(0xffffffffu, ok)) {
+          have = true;
+          break;
+        }
+      }
+      if (__any_sync(0xffffffffu, expired())) break;
+      __nanosleep(200);
+    }
+    if (!have) break;
+    __syncwarp();
+    const int qp = (t_x + 31) / 32;
+    uint32_t* dec = p.dec16 ? nullptr : sdec + static_cast<size_t>(g) * p.TXS;
+    uint16_t* ex = sexit + static_cast<size_t>(g) * p.TXS;
+    if (qp <= 1) walk_group<1>(stage, dec, ex, t_x, lane);
+    else if (qp <= 2) walk_group<2>(stage, dec, ex, t_x, lane);
+    else if (qp <= 4) walk_group<4>(stage, dec, ex, t_x, lane);
+    else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane);
+    else walk_group<8>(stage, dec, ex, t_x, lane);
+    __syncwarp();
+  }
+  while (!known) {  // (lazy form: every group that exists was walked before the lengths arrived)
+    poll_lens();
+    if (known || __any_sync(0xffffffffu, expired())) break;
+    __nanosleep(100);
+  }
+  if (!known) {  // gave up (`dead` is set): fall through to the barrier, after which nothing leaves this kernel
+    t_y = 1;
+    t_x = 1;
+  } else if (t_y <= 0) {  // invalid lengths: the path stays all-zero
     if (idx_b)
       for (int y = tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
     finish();
     return;
   }
   const int g_top = (t_y - 1) >> 5;
-  const uint2* bits_b = p.bits + static_cast<size_t>(b) * p.G * p.TXP;
-  const int nfw = (t_x + p.cols_per_warp - 1) / p.cols_per_warp;  // forward warps that write this utterance's words
-  uint32_t* stage = sstage + static_cast<size_t>(warp) * p.TXS;
-  const int qp = (t_x + 31) / 32;
-
-  for (int g = warp; g <= g_top; g += nw) {
-    const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
-    if (g < g_top) {
-      // wait for the group's words: an element is valid once it carries this call's tag.  Poll ONE element per
-      // forward warp (the last column it owns, or the last valid column) with back-off -- 1000 warps re-reading
-      // whole rows would saturate the L2 -- then read the row and check every tag.
-      for (;;) {
-        bool ok = true;
-        if (lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
-        if (__all_sync(0xffffffffu, ok)) {
-          for (int x = lane; x < t_x; x += 32) {
-            const uint2 el = load_tagged(row + x);
-            stage[x] = el.x;
-            ok = ok && el.y == tag;
-          }
-          if (__all_sync(0xffffffffu, ok)) break;
-        }
-        if (__any_sync(0xffffffffu, expired())) break;
-        __nanosleep(200);
+  if (warp == g_top % nw) {
+    // top group, whose entry (t_y-1, t_x-1) is known.  The walk can visit at most 32 columns; lane l
+    // holds the decision word of column t_x-1-l, 32 ballots transpose them into one mask per frame, and
+    // the walk itself is then pure register arithmetic (no dependent shared-memory loads).
+    const uint2* row = bits_b + static_cast<size_t>(g_top) * p.TXP;
+    const int rt = (t_y - 1) & 31;
+    const int col = t_x - 1 - lane;
+    uint32_t w = 0u;
+    for (;;) {
+      bool ok = true;
+      if (col >= 0) {
+        const uint2 el = load_tagged(row + col);
+        w = el.x;
+        ok = el.y == tag;
       }
-      __syncwarp();
-      uint32_t* dec = p.dec16 ? nullptr : sdec + static_cast<size_t>(g) * p.TXS;
-      uint16_t* ex = sexit + static_cast<size_t>(g) * p.TXS;
-      if (qp <= 1) walk_group<1>(stage, dec, ex, t_x, lane);
-      else if (qp <= 2) walk_group<2>(stage, dec, ex, t_x, lane);
-      else if (qp <= 4) walk_group<4>(stage, dec, ex, t_x, lane);
-      else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane);
-      else walk_group<8>(stage, dec, ex, t_x, lane);
-      __syncwarp();
-    } else {
-      // top group, whose entry (t_y-1, t_x-1) is known.  The walk can visit at most 32 columns; lane l
-      // holds the decision word of column t_x-1-l, 32 ballots transpose them into one mask per frame, and
-      // the walk itself is then pure register arithmetic (no dependent shared-memory loads).
-      const int rt = (t_y - 1) & 31;
-      const int col = t_x - 1 - lane;
-      uint32_t w = 0u;
-      for (;;) {
-        bool ok = true;
-        if (col >= 0) {
-          const uint2 el = load_tagged(row + col);
-          w = el.x;
-          ok = el.y == tag;
-        }
-        if (__all_sync(0xffffffffu, ok)) break;
-        if (__any_sync(0xffffffffu, expired())) break;
-        __nanosleep(50);
-      }
-      uint32_t pos = 0, decw = 0;
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (__any_sync(0xffffffffu, expired())) break;
+      __nanosleep(50);
+    }
+    uint32_t pos = 0, decw = 0;
 #pragma unroll
-      for (int r = 31; r >= 0; --r) {
-        const uint32_t m = __ballot_sync(0xffffffffu, (w >> (31 - r)) & 1u);  // bit l: decision of column t_x-1-l
-        if (r <= rt) {
-          const uint32_t d = (m >> pos) & 1u;
-          decw |= d << r;
-          pos += d;
-        }
+    for (int r = 31; r >= 0; --r) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (w >> (31 - r)) & 1u);  // bit l: decision of column t_x-1-l
+      if (r <= rt) {
+        const uint32_t d = (m >> pos) & 1u;
+        decw |= d << r;
+        pos += d;
       }
-      if (lane == 0) {
-        sentry[g_top] = t_x - 1;
-        if (!p.dec16) sdec[static_cast<size_t>(g_top) * p.TXS + t_x - 1] = decw;
-        smisc[2] = t_x - 1 - static_cast<int>(pos);  // entry of the group below
-        smisc[3] = static_cast<int>(decw);
-      }
+    }
+    if (lane == 0) {
+      sentry[g_top] = t_x - 1;
+      if (!p.dec16) sdec[static_cast<size_t>(g_top) * p.TXS + t_x - 1] = decw;
+      smisc[2] = t_x - 1 - static_cast<int>(pos);  // entry of the group below
+      smisc[3] = static_cast<int>(decw);
     }
   }
   __syncthreads();  // all tables are in shared memory
@@ -602,7 +643,7 @@ static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int 
 
 constexpr int kDp2Default = 33;  // mas_set_tuning3 `wavefront` value used when it is -1: mas_dp2 with the warmer
 // the second-generation wavefront kernel covers K = 2 (every automatic choice) unless the first one is asked for
-static bool dp2_selected(int K) { return K == 2 && g_tune_wf != 1 && ((g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & ~1) == 32; }
+static bool dp2_selected(int K) { return K == 2 && g_tune_wf != 1 && ((g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & ~7) == 32; }
 
 struct DpConfig {
   int K, W, S, BR, linear, skew;
@@ -890,7 +931,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     int dp2_hs = 0;
     if (!fused && dc.linear && dc.skew <= 2 && dp2_selected(dc.K)) {
       dp2_hs = 32;
-      dp.warm = (g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & 1;
+      dp.warm = (g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & 7;  // bit 0: instruction-cache warmer; bit 2: experiment (dummy mask walk)
     }
     if (!(g_debug_kernels & 8)) {  // (bit 3: watchdog test hook -- the backtrack kernel then never gets its words)
       e = dp2_hs ? launch_dp2_k2(tmap, dp, dc.skew, st)
@@ -990,6 +1031,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     sp.T_y = T_y; sp.T_x = T_x; sp.TXP = TXP; sp.G = L.G; sp.TXS = TXS;
     sp.cols_per_warp = cols_per_warp;
     sp.dec16 = dec16;
+    sp.lazy = wavefront ? 1 : 0;
     sp.es = es; sp.one = one_bits(path_dtype);
     sp.tl = g_timeline;
     // not co-resident with a forward CTA either (same trick as the write-out kernel)
