@@ -19,7 +19,7 @@ bufs = [torch.randn(B, T_y, T_x, generator=g, device='cuda') * 20 - 400 for _ in
 names = ['fwd first start (after griddepcontrol.wait)', 'fwd last DP warp done', 'fwd last end', 'bt first start',
          'bt last end', 'wo first start', 'wo last zero-fill done', 'lengths known']
 N = 4
-tls = [torch.zeros(8, dtype=torch.int64, device='cuda') for _ in range(N)]
+tls = [torch.zeros(16, dtype=torch.int64, device='cuda') for _ in range(N)]
 def reset():
     for tl in tls:
         tl.zero_(); tl[0] = tl[3] = tl[5] = -1
@@ -50,6 +50,9 @@ for rep in range(2):
     for i in range(N):
         row = "  ".join(f"{n.split(' (')[0]}={(int(x) - t0) / 1e3:7.2f}" for n, x in zip(names, v[i]) if int(x) not in (0, 2**64 - 1))
         print(f"  call {i}: {row}")
+        if int(v[i][8]):
+            print(f"          after the last DP warp: top group's words seen +{(int(v[i][8]) - int(v[i][1])) / 1e3:5.2f}, all tables done +{(int(v[i][9]) - int(v[i][1])) / 1e3:5.2f}, "
+                  f"last tabulated group's words complete +{(int(v[i][13]) - int(v[i][1])) / 1e3:5.2f}, its table +{(int(v[i][11]) - int(v[i][1])) / 1e3:5.2f}, top groups walked +{(int(v[i][12]) - int(v[i][1])) / 1e3:5.2f}, chain over groups done +{(int(v[i][10]) - int(v[i][1])) / 1e3:5.2f}, last backtrack CTA past its index/ones +{(int(v[i][4]) - int(v[i][1])) / 1e3:5.2f} us")
         print(f"          DP {(int(v[i][1]) - int(v[i][0])) / 1e3:6.2f} us, backtrack tail {(int(v[i][4]) - int(v[i][1])) / 1e3:6.2f} us, fill {(int(v[i][6]) - int(v[i][5])) / 1e3:6.2f} us")
     for i in range(1, N):
         last_end = max(int(v[i - 1][4]), int(v[i - 1][2]))

@@ -273,9 +273,12 @@ __device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, u
       for (int q = 0; q < QP; ++q) {
         uint32_t w;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr[q]));
-        const uint32_t bit = (w >> (31 - r)) & 1u;
-        dw[q] = dw[q] * 2u + bit;  // ends with the decision of frame r in bit r
-        addr[q] -= 4u * bit;
+        // one test and two predicated updates per step (the arithmetic form -- shift, mask, scale, add, twice -- was ~9
+        // instructions per step and entry column, and this walk is issue-bound: 1700 instructions = 2.7 us per group at c2)
+        if (w & (1u << (31 - r))) {
+          dw[q] |= 1u << r;  // the decision of frame r in bit r
+          addr[q] -= 4u;
+        }
       }
     }
 #pragma unroll
@@ -286,6 +289,8 @@ __device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, u
       }
   }
 }
+
+constexpr int kBallotGroups = 2;  // top groups walked from their single real entry instead of tabulated (see the kernel)
 
 __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     bool have = false;
     for (;;) {
       poll_lens();
-      if (known && (t_y <= 0 || g >= ((t_y - 1) >> 5))) break;  // the top group (handled below), or beyond it
+      if (known && (t_y <= 0 || g > ((t_y - 1) >> 5) - kBallotGroups)) break;  // one of the top groups (handled below), or beyond
       // wait for the group's words: an element is valid once it carries this call's tag.  Poll ONE element per
       // forward warp (the last column it owns, or the last valid column) with back-off -- 1000 warps re-reading
       // whole rows would saturate the L2 -- then read the row and check every tag.
@@ -377,10 +382,21 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
       bool ok = true;
       if (lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
       if (__all_sync(0xffffffffu, ok)) {
-        for (int x = lane; x < t_x; x += 32) {
-          const uint2 el = load_tagged(row + x);
-          stage[x] = el.x;
-          ok = ok && el.y == tag;
+        // the whole row, eight loads per lane in flight at once (one L2 round trip per 256 columns: as a plain loop the
+        // loads went out one after the other, six round trips at c2 -- ~1 us of every call's tail after the last frame)
+        for (int xb = 0; xb < t_x; xb += 256) {
+          uint2 el[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int x = xb + 32 * k + lane;
+            el[k] = x < t_x ? load_tagged(row + x) : make_uint2(0u, tag);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int x = xb + 32 * k + lane;
+            if (x < t_x) stage[x] = el[k].x;
+            ok = ok && el[k].y == tag;
+          }
         }
         if (__all_sync(0xffffffffu, ok)) {
           have = true;
@@ -388,9 +404,10 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
         }
       }
       if (__any_sync(0xffffffffu, expired())) break;
-      __nanosleep(200);
+      __nanosleep(100);
     }
     if (!have) break;
+    if (lane == 0) tl_max(p.tl, 13);  // (debug timeline) last time a tabulated group's words were complete
     __syncwarp();
     const int qp = (t_x + 31) / 32;
     uint32_t* dec = p.dec16 ? nullptr : sdec + static_cast<size_t>(g) * p.TXS;
@@ -401,6 +418,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane);
     else walk_group<8>(stage, dec, ex, t_x, lane);
     __syncwarp();
+    if (lane == 0) tl_max(p.tl, 11);  // ... and its table finished
   }
   while (!known) {  // (lazy form: every group that exists was walked before the lengths arrived)
     poll_lens();
@@ -418,42 +436,74 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
   }
   const int g_top = (t_y - 1) >> 5;
   if (warp == g_top % nw) {
-    // top group, whose entry (t_y-1, t_x-1) is known.  The walk can visit at most 32 columns; lane l
-    // holds the decision word of column t_x-1-l, 32 ballots transpose them into one mask per frame, and
-    // the walk itself is then pure register arithmetic (no dependent shared-memory loads).
-    const uint2* row = bits_b + static_cast<size_t>(g_top) * p.TXP;
-    const int rt = (t_y - 1) & 31;
-    const int col = t_x - 1 - lane;
-    uint32_t w = 0u;
-    for (;;) {
-      bool ok = true;
-      if (col >= 0) {
-        const uint2 el = load_tagged(row + col);
-        w = el.x;
-        ok = el.y == tag;
+    // The top kBallotGroups groups, one after the other from the known entry (t_y-1, t_x-1): a 32-frame walk can visit
+    // at most 32 columns; lane l holds the decision word of column entry-l, 32 ballots transpose them into one mask per
+    // frame, and the walk itself is then pure register arithmetic (no dependent shared-memory loads).  These are the
+    // groups whose words arrive last: tabulating them from every entry column, as the groups below are, ended 2.5 us after
+    // the top group's words had arrived -- on every call's critical path (tools/timeline_gap.py, profiles/r02as_tail.txt).
+    int entry = t_x - 1;
+    auto poll_cols = [&](int g, int e) {  // lane l: the word of column e-l of group g (0 left of column 0), once it is tagged
+      const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
+      const int col = e - lane;
+      uint32_t w = 0u;
+      for (;;) {
+        bool ok = true;
+        if (col >= 0) {
+          const uint2 el = load_tagged(row + col);
+          w = el.x;
+          ok = el.y == tag;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (__any_sync(0xffffffffu, expired())) break;
+        __nanosleep(50);
       }
-      if (__all_sync(0xffffffffu, ok)) break;
-      if (__any_sync(0xffffffffu, expired())) break;
-      __nanosleep(50);
-    }
-    uint32_t pos = 0, decw = 0;
-#pragma unroll
-    for (int r = 31; r >= 0; --r) {
-      const uint32_t m = __ballot_sync(0xffffffffu, (w >> (31 - r)) & 1u);  // bit l: decision of column t_x-1-l
-      if (r <= rt) {
-        const uint32_t d = (m >> pos) & 1u;
-        decw |= d << r;
-        pos += d;
+      return w;
+    };
+    uint32_t w = poll_cols(g_top, entry);
+    if (lane == 0) tl_max(p.tl, 8);  // (debug timeline) the top group's words have arrived
+    for (int g = g_top; g > g_top - kBallotGroups && g >= 0; --g) {
+      // The next group's entry lies within 32 columns of this one's: its 64 candidate words are requested NOW, so the
+      // L2 round trip overlaps this group's walk, and are shuffled into place once the exit is known.
+      const bool more = g - 1 > g_top - kBallotGroups && g - 1 >= 0;
+      uint2 ca = make_uint2(0u, tag), cb = make_uint2(0u, tag);
+      if (more) {
+        const uint2* nrow = bits_b + static_cast<size_t>(g - 1) * p.TXP;
+        if (entry - lane >= 0) ca = load_tagged(nrow + entry - lane);
+        if (entry - 32 - lane >= 0) cb = load_tagged(nrow + entry - 32 - lane);
+      }
+      const int rt = g == g_top ? (t_y - 1) & 31 : 31;
+      // (four steps per trip, not 32 unrolled: this runs once or twice per CTA, and code that runs once is fetched
+      // cold at ~16 cycles per instruction -- the unrolled form took ~1 us per group; and as few instructions per step
+      // as possible: a lone warp's dependent scalar code issues one instruction per ~5 cycles)
+      uint32_t decw = 0u, posbit = 1u;  // posbit = 1 << (columns stepped so far)
+#pragma unroll 4
+      for (int r = rt; r >= 0; --r) {
+        const uint32_t m = __ballot_sync(0xffffffffu, (w & (0x80000000u >> r)) != 0u);  // bit l: decision of column entry-l
+        if (m & posbit) {
+          decw |= 1u << r;
+          posbit <<= 1;
+        }
+      }
+      const uint32_t pos = static_cast<uint32_t>(__popc(decw));
+      if (lane == 0) {
+        sentry[g] = entry;
+        if (!p.dec16) sdec[static_cast<size_t>(g) * p.TXS + entry] = decw;
+        if (g == g_top) smisc[3] = static_cast<int>(decw);
+      }
+      entry -= static_cast<int>(pos);
+      if (more) {
+        const int k = static_cast<int>(pos) + lane;  // lane l now needs candidate column number pos+l
+        const uint32_t wa = __shfl_sync(0xffffffffu, ca.x, k & 31), wb = __shfl_sync(0xffffffffu, cb.x, k & 31);
+        const uint32_t ta = __shfl_sync(0xffffffffu, ca.y, k & 31), tb = __shfl_sync(0xffffffffu, cb.y, k & 31);
+        w = k < 32 ? wa : wb;
+        if (!__all_sync(0xffffffffu, (k < 32 ? ta : tb) == tag)) w = poll_cols(g - 1, entry);  // (not there yet)
       }
     }
-    if (lane == 0) {
-      sentry[g_top] = t_x - 1;
-      if (!p.dec16) sdec[static_cast<size_t>(g_top) * p.TXS + t_x - 1] = decw;
-      smisc[2] = t_x - 1 - static_cast<int>(pos);  // entry of the group below
-      smisc[3] = static_cast<int>(decw);
-    }
+    if (lane == 0) smisc[2] = entry;  // entry of the first tabulated group
+    if (lane == 0) tl_max(p.tl, 12);
   }
   __syncthreads();  // all tables are in shared memory
+  if (tid == 0) tl_max(p.tl, 9);
   if (*dead) {  // a poll gave up: nothing derived from incomplete words leaves this kernel
     if (idx_b)
       for (int y = tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
@@ -463,7 +513,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
   if (warp == 0) {
     // chain over the groups below the top one: entry - popc(decisions)
     int cur = smisc[2];
-    for (int g = g_top - 1; g >= 0; --g) {
+    for (int g = g_top - kBallotGroups; g >= 0; --g) {
       if (lane == 0) sentry[g] = cur;
       cur = p.dec16 ? static_cast<int>(sexit[static_cast<size_t>(g) * p.TXS + cur])
                     : cur - __popc(sdec[static_cast<size_t>(g) * p.TXS + cur]);
@@ -487,6 +537,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     finish();
     return;
   }
+  if (tid == 0) tl_max(p.tl, 10);  // chain over the groups done, zero-fill seen complete
   // per-frame index: entry of the frame's group minus the steps taken above the frame
   unsigned char* path_b = p.path ? p.path + static_cast<size_t>(b) * p.T_y * p.T_x * p.es : nullptr;
   if (!p.dec16) {
