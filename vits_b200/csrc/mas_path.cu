@@ -258,9 +258,9 @@ __device__ __forceinline__ void store_one(unsigned char* p, int es, unsigned lon
 // when leaving frame r".  The exit column is entry - popc(word); the column at frame r is
 // entry - popc(word >> (r+1)).
 template <int QP>
-__device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, uint16_t* ex, int t_x, int lane) {
+__device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, uint16_t* ex, int t_x, int lane, int e_lo = 0) {
   const uint32_t row_addr = ptx::smem_u32(row);
-  for (int e0 = lane; e0 < t_x; e0 += 32 * QP) {
+  for (int e0 = e_lo + lane; e0 < t_x; e0 += 32 * QP) {  // entry columns [e_lo, t_x)
     uint32_t addr[QP], dw[QP];
 #pragma unroll
     for (int q = 0; q < QP; ++q) {
@@ -290,7 +290,7 @@ __device__ __forceinline__ void walk_group(const uint32_t* row, uint32_t* dec, u
   }
 }
 
-constexpr int kBallotGroups = 2;  // top groups walked from their single real entry instead of tabulated (see the kernel)
+constexpr int kBallotGroups = 1;  // top groups walked from their single real entry instead of tabulated (see the kernel)
 
 __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -379,12 +379,17 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
       // forward warp (the last column it owns, or the last valid column) with back-off -- 1000 warps re-reading
       // whole rows would saturate the L2 -- then read the row and check every tag.
       const int nfw = (t_x + p.cols_per_warp - 1) / p.cols_per_warp;  // forward warps that write the words walked here
+      // columns needed: all of them -- or, with the lengths known, the reachable entry columns and the 32 to their left
+      // (see e_lo below).  A window of at most 256 columns (the groups next to the top: the ones the end of the call
+      // waits for) is read at once, without the one-element poll in front: one L2 round trip instead of two.
+      const int x_lo = known ? max(0, t_x - 1 - (t_y - 32 * (g + 1)) - 32) & ~31 : 0;
+      const bool direct = known && t_x - x_lo <= 256;
       bool ok = true;
-      if (lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
+      if (!direct && lane < nfw) ok = load_tagged(row + min((lane + 1) * p.cols_per_warp, t_x) - 1).y == tag;
       if (__all_sync(0xffffffffu, ok)) {
-        // the whole row, eight loads per lane in flight at once (one L2 round trip per 256 columns: as a plain loop the
-        // loads went out one after the other, six round trips at c2 -- ~1 us of every call's tail after the last frame)
-        for (int xb = 0; xb < t_x; xb += 256) {
+        // eight loads per lane in flight at once (one L2 round trip per 256 columns: as a plain loop the loads went out
+        // one after the other, six round trips at c2 -- ~1 us of every call's tail after the last frame)
+        for (int xb = x_lo; xb < t_x; xb += 256) {
           uint2 el[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -404,19 +409,23 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
         }
       }
       if (__any_sync(0xffffffffu, expired())) break;
-      __nanosleep(100);
+      __nanosleep(direct ? 40 : 100);
     }
     if (!have) break;
     if (lane == 0) tl_max(p.tl, 13);  // (debug timeline) last time a tabulated group's words were complete
     __syncwarp();
-    const int qp = (t_x + 31) / 32;
+    // Once the lengths are known, only the entry columns the path can reach matter: it enters group g at most
+    // t_y - 32(g+1) columns to the left of t_x-1.  For the groups next to the top that is a handful of columns -- one or
+    // two chains per lane instead of six at c2 -- and it is their tables the end of the call waits for.
+    const int e_lo = known ? max(0, t_x - 1 - (t_y - 32 * (g + 1))) : 0;
+    const int qp = (t_x - e_lo + 31) / 32;
     uint32_t* dec = p.dec16 ? nullptr : sdec + static_cast<size_t>(g) * p.TXS;
     uint16_t* ex = sexit + static_cast<size_t>(g) * p.TXS;
-    if (qp <= 1) walk_group<1>(stage, dec, ex, t_x, lane);
-    else if (qp <= 2) walk_group<2>(stage, dec, ex, t_x, lane);
-    else if (qp <= 4) walk_group<4>(stage, dec, ex, t_x, lane);
-    else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane);
-    else walk_group<8>(stage, dec, ex, t_x, lane);
+    if (qp <= 1) walk_group<1>(stage, dec, ex, t_x, lane, e_lo);
+    else if (qp <= 2) walk_group<2>(stage, dec, ex, t_x, lane, e_lo);
+    else if (qp <= 4) walk_group<4>(stage, dec, ex, t_x, lane, e_lo);
+    else if (qp <= 6) walk_group<6>(stage, dec, ex, t_x, lane, e_lo);
+    else walk_group<8>(stage, dec, ex, t_x, lane, e_lo);
     __syncwarp();
     if (lane == 0) tl_max(p.tl, 11);  // ... and its table finished
   }
