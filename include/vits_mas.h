@@ -217,14 +217,19 @@ void mas_set_debug_kernels(int mask);
  * forward kernel, 2 streaming backtrack kernel on the idle SMs while the forward kernel runs, 3 the same
  * behind the wavefront forward kernel; helpers: helper warps of the fused kernel (0 = automatic). */
 void mas_set_tuning2(int fused, int helpers);
-/* Wavefront forward kernel: wavefront 0 = never choose it automatically, -1 = automatic; ring_mode 1..3 =
+/* Wavefront forward kernel: wavefront 0 = never choose it automatically, -1 = automatic (the second-generation
+ * kernel mas_dp2_kernel where it applies: linear ring, two columns per lane, skew <= 2), 1 = the first-generation
+ * kernel mas_dp_kernel, 32 = mas_dp2_kernel, 33 = mas_dp2_kernel with its instruction-cache warmer (= automatic),
+ * 37 = 33 plus a dummy walk of the mask when the lengths are given (tools/mask_traffic.py); ring_mode 1..3 =
  * linear ring (mirror slot) with that many frames of skew between lanes, 4 = select ring (skew 1);
  * ring_slots = chunks of 32 frames per warp (>= skew + 2, or 3); cols_per_lane in {1,2,4}; 0 = automatic. */
 void mas_set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane);
-/* Debug timeline: device pointer to 8 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
- * kernels update with min start / max end %globaltimer stamps; NULL disables. */
+/* Debug timeline: device pointer to 16 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
+ * kernels update with min start / max end %globaltimer stamps (slots 8-13: phases of the backtrack kernel's
+ * tail, tools/timeline_gap.py); NULL disables. */
 void mas_set_timeline(void* dev_ptr);
-/* Debug event trace of the forward kernel's CTA 0: device pointer to 8*512*2 uint64 (zeroed), or NULL. */
+/* Debug event trace of the forward kernel's CTA 0 (-DMAS_TRACE builds, tools/trace_dp.py): device pointer to
+ * 8*512*2 uint64 (zeroed; the wavefront kernels use 8*256*8 + 2*B of them), or NULL. */
 void mas_set_trace(void* dev_ptr);
 
 #if defined(__GNUC__)

@@ -118,6 +118,35 @@ def test_wavefront_forward_kernel_configurations(mp, oracle, K, ring_mode):
         L.mas_set_tuning3(-1, 0, 0, 0)
 
 
+@pytest.mark.parametrize("wavefront", [1, 32, 33])
+def test_wavefront_kernel_generations(mp, oracle, wavefront):
+    """Both generations of the wavefront forward kernel (mas_set_tuning3: 1 = mas_dp_kernel, 32 = mas_dp2_kernel, 33 =
+    mas_dp2_kernel with the instruction-cache warmer = the automatic choice) against the oracle: ordinary values, ties,
+    values below the -1e9 sentinel (core.pyx:17-27 -- the diagonal and x == 0 rules are exercised exactly there), with
+    the lengths given and taken from the mask, skew 1 and 2."""
+    L = mp._lib.lib()
+    rng = np.random.default_rng(700 + wavefront)
+    try:
+        for shape in [(3, 200, 64), (2, 333, 100), (2, 900, 192), (2, 450, 256), (2, 40, 33), (1, 5, 4), (5, 1024, 192)]:
+            B, T_y, T_x = shape
+            for kind in ("normal", "ties", "subsentinel"):
+                if kind == "normal":
+                    nc = (rng.standard_normal(shape) * 3 - 4).astype(np.float32)
+                elif kind == "ties":
+                    nc = rng.integers(-3, 1, size=shape).astype(np.float32)
+                else:
+                    nc = (rng.standard_normal(shape) * 1e8 - 2e9).astype(np.float32)
+                t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+                want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+                for skew in (0, 1, 2):
+                    L.mas_set_tuning3(wavefront, skew, 0, 0)
+                    for via in ("mask", "lengths"):
+                        got = _gpu_path(mp, nc, t_ys, t_xs, via=via)
+                        np.testing.assert_array_equal(got, want, err_msg=f"wavefront={wavefront} skew={skew} {kind} {via} {shape}")
+    finally:
+        L.mas_set_tuning3(-1, 0, 0, 0)
+
+
 def test_streaming_backtrack_with_16_bit_tables(mp, oracle):
     """Long utterances: the streaming backtrack keeps 16-bit exit columns and re-walks the groups."""
     L = mp._lib.lib()

@@ -11,7 +11,7 @@ ty = torch.full((B,), T_y, dtype=torch.int32).cuda(); tx = torch.full((B,), T_x,
 g = torch.Generator(device='cuda').manual_seed(1)
 bufs = [torch.randn(B, T_y, T_x, generator=g, device='cuda') * 20 - 400 for _ in range(3)]
 L.mas_set_debug_kernels(1); L.mas_set_tuning(K, mode, 0, 0)
-tl = torch.zeros(8, dtype=torch.int64, device='cuda')
+tl = torch.zeros(16, dtype=torch.int64, device='cuda')
 res = []
 for i in range(4):
     tl.zero_(); tl[0] = -1; torch.cuda.synchronize(); L.mas_set_timeline(tl.data_ptr())

@@ -16,7 +16,7 @@ g = torch.Generator(device='cuda').manual_seed(1)
 bufs = [torch.randn(B, T_y, T_x, generator=g, device='cuda') * 20 - 400 for _ in range(4)]
 names = ['fwd first start', 'fwd last DP warp done', 'fwd last end', 'bt first start', 'bt last end',
          'wo first start', 'wo last zero-fill done', 'wo last end']
-tl = torch.zeros(8, dtype=torch.int64, device='cuda')
+tl = torch.zeros(16, dtype=torch.int64, device='cuda')
 def reset():
     tl.zero_(); tl[0] = tl[3] = tl[5] = -1   # uint64 max for the "min" slots
 def show(tag):

@@ -15,7 +15,7 @@ for ragged in (True, False):
     sets = [(torch.randn(B, 192, T_y, generator=g, device="cuda"), torch.randn(B, 192, T_x, generator=g, device="cuda"),
              torch.randn(B, 192, T_x, generator=g, device="cuda") * 0.3) for _ in range(3)]
     ty, tx = torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()
-    tl = torch.zeros(8, dtype=torch.int64, device="cuda")
+    tl = torch.zeros(16, dtype=torch.int64, device="cuda")
     runs = []
     for i in range(6):
         tl.zero_(); tl[0] = tl[3] = tl[5] = -1

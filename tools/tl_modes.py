@@ -14,7 +14,7 @@ ty, tx = torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()
 mask = ((torch.arange(T_y, device='cuda')[None, :] < ty[:, None])[:, :, None] & (torch.arange(T_x, device='cuda')[None, :] < tx[:, None])[:, None, :]).float()
 g = torch.Generator(device='cuda').manual_seed(1)
 bufs = [torch.randn(B, T_y, T_x, generator=g, device='cuda') * 20 - 400 for _ in range(3)]
-tl = torch.zeros(8, dtype=torch.int64, device='cuda')
+tl = torch.zeros(16, dtype=torch.int64, device='cuda')
 names = ["dp_start", "dp_done", "fwd_end", "bt_start", "bt_end", "fill_start", "fill_done", "wo_end"]
 call = (lambda nc: vits_b200.maximum_path(nc, mask)) if use_mask else (lambda nc: vits_b200.maximum_path_from_lengths(nc, ty, tx))
 if index_only: call = lambda nc: vits_b200.maximum_path_index(nc, y_lengths=ty, x_lengths=tx)
