@@ -655,15 +655,15 @@ def run_ours(args, rank, world, local_rank):
         # DRAM bytes of one step's three kernels from `ncu --set full` (profiles/): only captured for c2, B = 64
         traffic, traffic_note = None, "not captured for this workload"
         if args.workload == "c2" and primary_ragged:
-            traffic = 43.77e6 + 50.33e6
-            traffic_note = ("c2 variable lengths, profiles/r01_g_chain_c2_variable_lengths.ncu-rep: dram read+write inside the "
-                            "kernels' windows = mas_dp 40.79 MB (30.6 MB algorithmic: 32x64 TMA boxes overhang the band "
-                            "and t_x) + mas_writeout 0.87 MB + mas_backtrack_stream 2.11 MB = 43.77 MB, plus the 50.33 MB "
-                            "dense path that ncu sees absorbed by the 126 MB L2 and that is written back after the "
-                            "window (counted here once, as it must reach HBM)")
+            traffic = 44.20e6 + 50.33e6
+            traffic_note = ("c2 variable lengths, profiles/r02_final_chain_c2_variable_lengths_summary.txt (ncu --set full over one "
+                            "call's three kernels): dram read+write inside the kernels' windows = mas_dp2 40.80 MB (30.6 MB "
+                            "algorithmic: 32x64 TMA boxes overhang the band and t_x) + mas_writeout 1.40 MB + "
+                            "mas_backtrack_stream 2.02 MB = 44.2 MB, plus the 50.33 MB dense path that ncu sees absorbed by the "
+                            "126 MB L2 and that is written back after the window (counted here once, as it must reach HBM)")
         elif args.workload == "c2":
             traffic = 105.4e6
-            traffic_note = ("full-length c2, profiles/r01_f_mas_dp_summary.txt: mas_dp 50.4 MB DRAM read + 1.6 MB of tagged "
+            traffic_note = ("full-length c2, profiles/r02_final_mas_dp2_summary.txt: mas_dp2 50.4 MB DRAM read + 1.6 MB of tagged "
                             "decision words (and 3.1 MB of tag clears), mas_writeout 50.3 MB written")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
