@@ -118,16 +118,18 @@ def test_wavefront_forward_kernel_configurations(mp, oracle, K, ring_mode):
         L.mas_set_tuning3(-1, 0, 0, 0)
 
 
-@pytest.mark.parametrize("wavefront", [1, 32, 33])
+@pytest.mark.parametrize("wavefront", [1, 32, 33, 41, 49])
 def test_wavefront_kernel_generations(mp, oracle, wavefront):
     """Both generations of the wavefront forward kernel (mas_set_tuning3: 1 = mas_dp_kernel, 32 = mas_dp2_kernel, 33 =
-    mas_dp2_kernel with the instruction-cache warmer = the automatic choice) against the oracle: ordinary values, ties,
-    values below the -1e9 sentinel (core.pyx:17-27 -- the diagonal and x == 0 rules are exercised exactly there), with
-    the lengths given and taken from the mask, skew 1 and 2."""
+    mas_dp2_kernel with the instruction-cache warmer = the automatic choice: one CTA per utterance up to four DP warps,
+    a cluster of two beyond; 41 = never a cluster, 49 = a cluster whenever the text has two warps) against the oracle:
+    ordinary values, ties, values below the -1e9 sentinel (core.pyx:17-27 -- the diagonal and x == 0 rules are exercised
+    exactly there), with the lengths given and taken from the mask, skew 1 and 2."""
     L = mp._lib.lib()
     rng = np.random.default_rng(700 + wavefront)
     try:
-        for shape in [(3, 200, 64), (2, 333, 100), (2, 900, 192), (2, 450, 256), (2, 40, 33), (1, 5, 4), (5, 1024, 192)]:
+        for shape in [(3, 200, 64), (2, 333, 100), (2, 900, 192), (2, 450, 256), (2, 40, 33), (1, 5, 4), (5, 1024, 192),
+                      (2, 700, 300), (2, 600, 512), (3, 520, 449)]:
             B, T_y, T_x = shape
             for kind in ("normal", "ties", "subsentinel"):
                 if kind == "normal":

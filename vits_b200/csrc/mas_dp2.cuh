@@ -25,15 +25,24 @@
 
 namespace mas {
 
-template <int K, int D>
-__global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__ CUtensorMap tmap, const DpParams p) {
+template <int K, int D, int CL>
+__global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __grid_constant__ CUtensorMap tmap, const DpParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int R = kRows;
   constexpr int Q = (31 * D + 31) / 32;        // chunks (and decision-word groups) a superstep reaches back
   constexpr int LAG = (30 + 31 * D) / 32 + 1;  // supersteps the left neighbour must be ahead
   constexpr uint32_t ROWB = 32u * K * 4u;      // bytes of one ring row: this warp's 32*K columns of one frame
   constexpr uint32_t SLOTB = R * ROWB;
-  const int b = blockIdx.x;
+  // CL > 1: an utterance's columns are split over a cluster of CL CTAs (W = DP warps of THIS CTA, global warp index
+  // gw0 + dw): the last column crosses the CTA boundary through distributed shared memory, by READS only -- the right
+  // CTA's first warp loads its hand-off blocks and the left neighbour's progress counter from the left CTA's shared
+  // memory (two blocks ahead: a remote load takes ~215 cycles), the left CTA's last warp reads the right neighbour's
+  // counter there.  (Remote STORES were tried first: a store per step through shared::cluster cost ~20 cycles each and
+  // the fence.acq_rel.cluster in front of the progress store 0.7 us per superstep: c3 94 instead of 43 us.)  A text of
+  // 512 tokens is then four DP warps per SM (one per scheduler, linear ring) instead of eight on one SM with the
+  // select ring of the first generation.
+  const int rank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int b = CL > 1 ? blockIdx.x / CL : blockIdx.x;
   const int tid = threadIdx.x;
   const int wid = tid >> 5;
   const bool spread = p.W <= 3;  // warp roles exactly as in mas_dp_kernel
@@ -41,6 +50,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   int dw = spread ? (wid < 3 ? (wid < p.W ? wid : -1) : (wid & 3) == 3 ? p.W + (wid >> 2) : -1) : wid;
   const int lane = tid & 31;
   const int S = p.S, W = p.W, BR = p.BR;
+  const int gw0 = rank * W;  // global index of this CTA's first DP warp
   const int nphys = S + 1;
   // the instruction-cache warmer: an idle warp on the scheduler of the last DP warp (which starts last)
   const bool shadow = (p.warm & 1) != 0 && spread && wid == (W < 3 ? 4 + W : 6);
@@ -59,10 +69,10 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   const long long rows_total = static_cast<long long>(p.B) * p.T_y;
   auto copy_chunk = [&](int w, int c, unsigned char* dst, uint64_t* bar) {
     if (p.use_tma) {
-      if (lane == 0) ptx::tma_load_2d(dst, &tmap, w * 32 * K, b * p.T_y + c * R, bar);
+      if (lane == 0) ptx::tma_load_2d(dst, &tmap, (gw0 + w) * 32 * K, b * p.T_y + c * R, bar);
     } else {
       const uint32_t d0 = ptx::smem_u32(dst) + static_cast<uint32_t>(lane) * K * 4u;
-      const int xb = (w * 32 + lane) * K;
+      const int xb = ((gw0 + w) * 32 + lane) * K;
 #pragma unroll 2
       for (int r = 0; r < R; ++r) {
         const long long grow = static_cast<long long>(b) * p.T_y + c * R + r;
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     for (int c = 0; c < nspec; ++c)
       for (int w = 0; w < W; ++w) issue_chunk(w, c, c);
   }
-  if (b == 0 && tid == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     p.wo_counters[0] = 0;
     p.wo_counters[1] = 0;
   }
@@ -104,8 +114,8 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   if (p.lenstag) {
     uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
     const int n16 = p.G * p.TXP / 2;
-    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
+    for (int i = tid + rank * blockDim.x; i < n16; i += blockDim.x * CL) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0 && rank == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
   }
   if (tid == 0) tl_min(p.tl, 0);
 #ifdef MAS_TRACE
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before the TMA's later writes
   }
-  for (int i = tid; i < (W + 1) * BR; i += blockDim.x) bnd[i] = (i == 0) ? 0.0f : kNeg;  // (0,0): v_prev = 0 (core.pyx:22-23)
+  for (int i = tid; i < (W + 1) * BR; i += blockDim.x) bnd[i] = (i == 0 && rank == 0) ? 0.0f : kNeg;  // (0,0): v_prev = 0 (core.pyx:22-23)
   if (tid < W) prog[tid] = 0;
   volatile int* lens_v = lens_s;  // [0] t_y, [1] t_x, [2] 1 once they are known
   if (tid == 0) {
@@ -133,6 +143,18 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     red[1] = 0.0;
   }
   __syncthreads();
+  // A peer reads this CTA's hand-off ring and progress counters: nobody starts before both CTAs are initialised, and
+  // nobody leaves (leave() below) before both are done.
+  if (CL > 1) {
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  }
+  auto leave = [&]() {
+    if (CL > 1) {
+      ptx::cluster_arrive();
+      ptx::cluster_wait();
+    }
+  };
 
   // Lengths: one warp publishes them; when they come from the mask (monotonic_align/__init__.py:17-18) the
   // otherwise idle warps of the CTA help with the strided walk over column 0 -- 1024 sectors per utterance, one DRAM
@@ -140,7 +162,10 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   const bool lenw = dw == W + NP;
   const bool dummy_walk = (p.warm & 4) != 0 && p.t_ys != nullptr && p.mask != nullptr;  // (experiment: the walk's traffic alone)
   const bool helper = spread && dw < 0 && !shadow && (p.t_ys == nullptr || dummy_walk);
-  if (dw < 0 && !shadow && !helper) return;  // filler warps
+  if (dw < 0 && !shadow && !helper) {  // filler warps
+    leave();
+    return;
+  }
   if (lenw || helper) {
     if (lenw && lane == 0) {
       __threadfence();  // tags and counters were cleared before the barrier: visible GPU-wide before the dependents start
@@ -151,19 +176,19 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
       t_y = p.t_ys[b];
       t_x = p.t_xs[b];
     } else {
-      int nh = 0, rank = 0;  // warps that walk the mask, and this warp's place among them
+      int nh = 0, hrank = 0;  // warps that walk the mask, and this warp's place among them
       if (spread) {
         for (int u = 0; u < 12; ++u) {
           const bool sh = (p.warm & 1) != 0 && u == (W < 3 ? 4 + W : 6);
           const bool part = u == 11 || (!sh && ((u < 3 && u >= W) || (u > 3 && (u & 3) != 3)));
           nh += part ? 1 : 0;
-          rank += part && u < wid ? 1 : 0;
+          hrank += part && u < wid ? 1 : 0;
         }
       } else {
         nh = 1;
       }
       double sy, sx;
-      mask_sums(p.mask, p.mask_dtype, static_cast<int64_t>(b) * p.msb, p.msy, p.T_y, p.msx, p.T_x, rank * 32 + lane, nh * 32, sy, sx);
+      mask_sums(p.mask, p.mask_dtype, static_cast<int64_t>(b) * p.msb, p.msy, p.T_y, p.msx, p.T_x, hrank * 32 + lane, nh * 32, sy, sx);
       sy = warp_sum(sy);
       sx = warp_sum(sx);
       if (nh > 1) {
@@ -173,7 +198,10 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
           __threadfence_block();
           atomicAdd(&lens_s[3], 1);
         }
-        if (!lenw) return;
+        if (!lenw) {
+          leave();
+          return;
+        }
         if (lane == 0)
           while (ptx::ld_volatile_s32(&lens_s[3]) < nh) {
             __nanosleep(200);
@@ -191,17 +219,20 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     if (t_x > t_y) st |= MAS_STATUS_TX_GT_TY;
     if (st) t_y = t_x = 0;
     if (lane == 0) {
-      if (st) raise_status(p.status, p.mirror, st);
-      p.lens[2 * b] = t_y;
-      p.lens[2 * b + 1] = t_x;
-      if (p.lenstag)
-        *reinterpret_cast<unsigned long long*>(p.lenstag + b) = pack_tagged((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), tag);
+      if (rank == 0) {  // (every CTA of a cluster finds the lengths for itself; the first one publishes them)
+        if (st) raise_status(p.status, p.mirror, st);
+        p.lens[2 * b] = t_y;
+        p.lens[2 * b + 1] = t_x;
+        if (p.lenstag)
+          *reinterpret_cast<unsigned long long*>(p.lenstag + b) = pack_tagged((static_cast<uint32_t>(t_y) << 12) | static_cast<uint32_t>(t_x), tag);
+      }
       lens_v[0] = t_y;
       lens_v[1] = t_x;
       __threadfence_block();
       lens_v[2] = 1;
       tl_max(p.tl, 7);
     }
+    leave();
     return;
   }
   bool known = false;
@@ -227,7 +258,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
       const bool ready = want && ptx::ld_volatile_s32(&prog[lane]) >= ci - S + Q + 1;
       unsigned m = __ballot_sync(0xffffffffu, ready);
       if (known && !__any_sync(0xffffffffu, mine && ci < nchunks)) break;
-      if (m == 0u) __nanosleep(64);
+      if (m == 0u) __nanosleep(64);  // (64..200 ns measure the same in the wide layout, where producers share the DP warps' schedulers)
       while (m) {
         const int w = __ffs(m) - 1;
         m &= m - 1;
@@ -242,21 +273,35 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     }
     if (mine)
       for (int c = max(nchunks, ci - S); c < ci; ++c) ptx::mbar_wait(full_all + static_cast<size_t>(lane) * S + (c % S), (c / S) & 1);
+    leave();
     return;
   }
 
   // ---- DP warp (and the warmer, which runs one superstep of the plain variant on whatever the ring holds and
   // touches nothing outside its registers) ----
-  const int x0 = (dwa * 32 + lane) * K;
-  const bool has_left = dwa > 0;
-  const bool has_right = dwa < W - 1 && !shadow;
+  const int gw = gw0 + dwa;  // this warp's place among the utterance's DP warps
+  const int x0 = (gw * 32 + lane) * K;
+  const bool has_left = gw > 0;
+  const bool has_right = gw < W * CL - 1 && !shadow;
+  // progress of the neighbours and the left edge: this CTA's shared memory, or (CL > 1, the warps either side of the
+  // CTA boundary) the neighbouring CTA's, as shared::cluster addresses
+  const bool in_remote = CL > 1 && dwa == 0 && rank > 0;
+  const bool right_remote = CL > 1 && dwa == W - 1 && rank < CL - 1;
+  const int* plp = &prog[dwa > 0 ? dwa - 1 : 0];
+  const int* prp = &prog[dwa < W - 1 ? dwa + 1 : 0];
+  const uint32_t plc = CL > 1 ? (in_remote ? ptx::mapa(ptx::smem_u32(&prog[W - 1]), rank - 1) : ptx::mapa(ptx::smem_u32(plp), rank)) : 0u;
+  const uint32_t prc = CL > 1 ? (right_remote ? ptx::mapa(ptx::smem_u32(&prog[0]), rank + 1) : ptx::mapa(ptx::smem_u32(prp), rank)) : 0u;
+  auto ld_left = [&]() { return CL > 1 ? ptx::ld_volatile_cluster_s32(plc) : ptx::ld_volatile_s32(plp); };
+  auto ld_right = [&]() { return CL > 1 ? ptx::ld_volatile_cluster_s32(prc) : ptx::ld_volatile_s32(prp); };
   const bool lane0 = lane == 0;
   const bool lane31 = lane == 31 && !shadow;
-  const uint32_t bnd_in = ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR);
+  const uint32_t bnd_in = CL > 1 ? (in_remote ? ptx::mapa(ptx::smem_u32(bnd + static_cast<size_t>(W) * BR), rank - 1)
+                                            : ptx::mapa(ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR), rank))
+                                 : ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR);
   float* bnd_out = bnd + static_cast<size_t>(dwa + 1) * BR;
   uint2* bits_b = reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP + x0;  // {word, tag} pairs
   const int dt = x0 + D * lane;
-  const int diag_lo = dwa * 32 * K, diag_hi = dwa * 32 * K + 31 * (K + D) + K - 1;
+  const int diag_lo = gw * 32 * K, diag_hi = gw * 32 * K + 31 * (K + D) + K - 1;
   const int hsel = (D * lane) >> 5;
   const int hsh = (D * lane) & 31;
 
@@ -278,18 +323,22 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
   int ls = 0;
   uint32_t par = 0u;
 
-  float cb[4][K], e[2][8];
+  constexpr int NE = CL > 1 ? 4 : 2;  // hand-off blocks of 8 frames held in registers ...
+  constexpr int AH = CL > 1 ? 2 : 1;  // ... loaded this many blocks ahead of their use
+  float cb[4][K], e[NE][8];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int j = 0; j < K; ++j) cb[k][j] = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) e[0][k] = e[1][k] = kNeg;
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int q = 0; q < NE; ++q) e[q][k] = kNeg;
   bool pre = false;
 
   auto load_e = [&](uint32_t a, float (&e8)[8]) {
-    const float4 e0 = ptx::lds_f32x4(a);
-    const float4 e1 = ptx::lds_f32x4(a + 16u);
+    const float4 e0 = CL > 1 ? ptx::ld_cluster_f32x4(a) : ptx::lds_f32x4(a);
+    const float4 e1 = CL > 1 ? ptx::ld_cluster_f32x4(a + 16u) : ptx::lds_f32x4(a + 16u);
     e8[0] = e0.x; e8[1] = e0.y; e8[2] = e0.z; e8[3] = e0.w;
     e8[4] = e1.x; e8[5] = e1.y; e8[6] = e1.z; e8[7] = e1.w;
   };
@@ -333,16 +382,17 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     int fl = 0;
     if (has_left) {
       for (;;) {
-        fl = ptx::ld_volatile_s32(&prog[dwa - 1]);
+        fl = ld_left();
         if (fl >= min(s + LAG, NS)) break;
         check_lens();  // the neighbour may have stopped at a smaller NS than the one assumed so far
       }
     }
     if (has_right && need_r > 0)
-      while (ptx::ld_volatile_s32(&prog[dwa + 1]) < need_r) {
+      while (ld_right() < need_r) {
       }
     ea += static_cast<uint32_t>(fl) >> 31;  // (null) dependency: the hand-off loads stay behind the poll
-    load_e(ea, e[0]);
+#pragma unroll
+    for (int q = 0; q < AH; ++q) load_e(ea + 32u * q, e[q]);
   };
 
   // One superstep = one basic block: the previous superstep's decision words, this superstep's addresses and
@@ -367,8 +417,9 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     const uint32_t ea_n = bnd_in + 4u * static_cast<uint32_t>((32 * s + 32) & (BR - 1));
     const int need_r = s - BR / 32 + 1;
     constexpr int R0 = 32 * Q - (31 * D - 1);  // lane 31 publishes frame 32s+i-31D into slot 32(s-Q) + R0 + i
-    float* bo1 = bnd_out + ((32 * (s - Q)) & (BR - 1)) + R0;
-    float* bo2 = bnd_out + ((32 * (s - Q + 1)) & (BR - 1)) - (32 - R0);
+    const int bi1 = ((32 * (s - Q)) & (BR - 1)) + R0, bi2 = ((32 * (s - Q + 1)) & (BR - 1)) - (32 - R0);
+    float* bo1 = bnd_out + bi1;
+    float* bo2 = bnd_out + bi2;
     const int dd = dt - 32 * s;
     bool chunk_n = true;
     int pl = 0x7fffffff, pr = 0x7fffffff;
@@ -377,18 +428,18 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     for (int i = 0; i < 32; ++i) {
       lds_cols<K>(cb[(i + 3) & 3], (i + 3 < 32 ? pcur : pcur_n - 32u * ROWB) + static_cast<uint32_t>(i + 3) * ROWB);
       if ((i & 7) == 0) {
-        const int blk = i / 8 + 1;
-        load_e(blk < 4 ? ea + 32u * blk : ea_n + dep, e[blk & 1]);
+        const int blk = i / 8 + AH;  // (blocks 4, 5 are the next superstep's 0, 1)
+        load_e(blk < 4 ? ea + 32u * blk : ea_n + 32u * (blk - 4) + dep, e[blk & (NE - 1)]);
       }
       if (i == 8) {  // non-blocking probes of the next superstep's inputs
         if (s + 1 < nchunks) chunk_n = ptx::mbar_test(&full[ls_n], par_n);
-        if (has_left) pl = ptx::ld_volatile_s32(&prog[dwa - 1]);
-        if (has_right) pr = ptx::ld_volatile_s32(&prog[dwa + 1]);
+        if (has_left) pl = ld_left();
+        if (has_right) pr = ld_right();
         dep = static_cast<uint32_t>(pl) >> 31;  // (null) dependency: the prefetch of the next block 0 stays behind this probe
       }
       const float (&c)[K] = cb[i & 3];
       const float nxt = __shfl_up_sync(0xffffffffu, v[K - 1], 1);  // for step i+D
-      const float le = lane0 ? e[(i / 8) & 1][i & 7] : left[0];
+      const float le = lane0 ? e[(i / 8) & (NE - 1)][i & 7] : left[0];
       if (DIAG) {
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) v[jj] = (i == dd + jj) ? kNeg : v[jj];  // core.pyx:17-18
@@ -444,7 +495,7 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
       if (s >= sd0 && s <= sd1) superstep(s, std::true_type{});
       else superstep(s, std::false_type{});
       ++s;
-      if (s == 1 && dwa == 0 && lane0 && !shadow) bnd[0] = kNeg;  // the (0,0) special case is consumed
+      if (s == 1 && gw == 0 && lane0 && !shadow) bnd[0] = kNeg;  // the (0,0) special case is consumed
       if (pre && known && s < NS) continue;  // the common case: everything the next superstep needs is there
       if (!known) check_lens();
       if (s >= NS) {
@@ -456,33 +507,48 @@ __global__ void __launch_bounds__(416, 1) mas_dp2_kernel(const __grid_constant__
     }
     if (!shadow) emit_words(s - 1 - Q, s - 1 >= Q);  // the last group's words
   }
-  if (shadow) return;
+  if (shadow) {
+    leave();
+    return;
+  }
   if (lane0) tl_max(p.tl, 1);
   if (lane0) tl_max(p.tl, 2);
 #ifdef MAS_TRACE
   if (p.trace && lane0) atomicMax(p.trace + 8 * 256 * 8 + 2 * b + 1, globaltimer_ns());
 #endif
+  leave();
 }
 
-template <int K, int D>
+template <int K, int D, int CL>
 inline cudaError_t launch_dp2_t(const CUtensorMap& tmap, const DpParams& p, cudaStream_t st) {
-  auto kern = mas_dp2_kernel<K, D>;
+  auto kern = mas_dp2_kernel<K, D, CL>;
   static std::atomic<uint64_t> attr_set{0};
   if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024, attr_set); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.B);
+  cfg.gridDim = dim3(p.B * CL);
   cfg.blockDim = dim3(p.W <= 3 ? 32 * 12 : 32 * (p.W + 4 + 1));
   cfg.dynamicSmemBytes = p.sm.total;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, tmap, p);
 }
 
-// K = 2 only (the automatic choice for every T_x the wavefront kernel covers); skew 1 or 2
-cudaError_t launch_dp2_k2(const CUtensorMap& tmap, const DpParams& p, int skew, cudaStream_t st);
+// K = 2 only (the automatic choice for every T_x the wavefront kernel covers); skew 1 or 2; cl = CTAs per utterance (1, 2)
+cudaError_t launch_dp2_k2(const CUtensorMap& tmap, const DpParams& p, int skew, int cl, cudaStream_t st);
 
 }  // namespace mas

@@ -701,13 +701,17 @@ static cudaError_t launch_fwd_dispatch(int K, bool vec, const FwdParams& p, int 
   }
 }
 
+constexpr int kDp2ClusterFromWarps = 5;  // DP warps (64 columns each) from which an utterance is split over two CTAs
+                                         // (measured: c3's four warps 42.7 us on one CTA, 49.8 us split; c4's eight 188 vs 129 us)
 constexpr int kDp2Default = 33;  // mas_set_tuning3 `wavefront` value used when it is -1: mas_dp2 with the warmer
 // the second-generation wavefront kernel covers K = 2 (every automatic choice) unless the first one is asked for
-static bool dp2_selected(int K) { return K == 2 && g_tune_wf != 1 && ((g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & ~7) == 32; }
+static bool dp2_selected(int K) { return K == 2 && g_tune_wf != 1 && ((g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & ~31) == 32; }
+static int dp2_flags() { return (g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & 31; }  // 1 warmer, 4 dummy mask walk, 8 never a cluster, 16 always
 
 struct DpConfig {
-  int K, W, S, BR, linear, skew;
+  int K, W, S, BR, linear, skew;  // W: DP warps per CTA
   DpSmem sm;
+  int CL;  // CTAs per utterance (mas_dp2 only): the text's columns split over a cluster
 };
 
 // Backtrack warps per CTA when the source is streamed: small batches leave SMs to spare (a CTA of 16 warps per
@@ -731,7 +735,7 @@ static DpSmem dp_smem_layout(int K, int W, int nphys, int S, int BR) {
 // A superstep of a warp reads frames 32s-31*D .. 32s+31 (D = skew between lanes): Q+1 = ceil(31D/32)+1 chunks
 // are live and at least one more must be in flight, so the linear ring needs S >= Q+2 slots plus the mirror;
 // the select ring (D = 1, no mirror) needs 3.  D = 3 hides the SHFL latency completely, D = 1 not at all.
-static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 208 * 1024) {
+static bool pick_dp_config_cl(int T_y, int T_x, DpConfig* cfg, uint32_t budget, int CL) {
   int K = g_tune_wfK;
   if (K == 0) K = 2;  // K = 2 keeps the per-step dependency chain short and fills one scheduler per 64 columns
   if (K != 1 && K != 2 && K != 4) return false;
@@ -741,6 +745,10 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 20
     W = (T_x + 32 * K - 1) / (32 * K);
   }
   if (W > 8) return false;
+  if (CL > 1) {
+    if (!dp2_selected(K) || W < CL) return false;
+    W = (W + CL - 1) / CL;  // DP warps per CTA
+  }
   const int BR = 256;
   if (budget < 48 * 1024) return false;
   const uint32_t slotset = static_cast<uint32_t>(W) * kRows * 32u * K * 4u;  // one chunk of every warp
@@ -756,6 +764,7 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 20
   else if (nphys >= 5 && W <= 3 && !dp2_selected(K)) skew = 2;
   else if (nphys >= 4) skew = 1;
   else { linear = 0; skew = 1; }
+  if (CL > 1 && (!linear || skew > 2)) return false;
   const int Q = (31 * skew + 31) / 32;
   const int smin = linear ? Q + 2 : 3;
   int S = linear ? nphys - 1 : nphys;
@@ -765,8 +774,18 @@ static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 20
   const DpSmem m = dp_smem_layout(K, W, linear ? S + 1 : S, S, BR);
   if (m.total > kSmemMax) return false;
   (void)T_y;
-  *cfg = DpConfig{K, W, S, BR, linear, skew, m};
+  *cfg = DpConfig{K, W, S, BR, linear, skew, m, CL};
   return true;
+}
+
+// Clusters (mas_dp2 only): automatic when the text needs four or more DP warps -- two CTAs of W/2 warps keep one DP warp
+// per scheduler and the linear ring (c4: eight warps on one SM with the select ring otherwise).
+static bool pick_dp_config(int T_y, int T_x, DpConfig* cfg, uint32_t budget = 208 * 1024, bool allow_cluster = true) {
+  const int Wt = (T_x + 63) / 64;
+  const int fl = dp2_flags();
+  const bool want2 = allow_cluster && !(fl & 8) && ((fl & 16) ? Wt >= 2 : Wt >= kDp2ClusterFromWarps);
+  if (want2 && pick_dp_config_cl(T_y, T_x, cfg, budget, 2)) return true;
+  return pick_dp_config_cl(T_y, T_x, cfg, budget, 1);
 }
 
 static cudaError_t launch_dp_dispatch(int K, const CUtensorMap& tmap, const DpParams& p, int skew, bool linear, cudaStream_t st) {
@@ -926,7 +945,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   // (Streamed source: a backtrack CTA sharing an SM with a forward CTA was measured to stretch the DP from 70 to 100 us
   // at c2 -- its sixteen, even eight, polling and walking warps take the DP warps' issue slots -- so, exactly as in the
   // ordinary mode, the forward CTAs fill their SM's shared memory and the backtrack CTAs run elsewhere.)
-  const bool wf_ok = stream_ok && T_x <= 512 && pick_dp_config(T_y, T_x, &dc);
+  const bool wf_ok = stream_ok && T_x <= 512 && pick_dp_config(T_y, T_x, &dc, 208 * 1024, fused == nullptr);
   if (fused) {
     if (!wf_ok || !dc.linear || dc.skew > 2 || !t_ys || !path_out || B + fused->reserve_ctas > g_num_sms ||
         (fused->pitch & 3) || (reinterpret_cast<uintptr_t>(fused->ring) & 15u))
@@ -943,7 +962,7 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   if (mode < 0 && !fc.fused && stream_ok) mode = 2;
   const bool stream = mode == 2 || mode == 3;
   const bool wavefront = mode == 3;
-  const int TXP = wavefront ? dc.W * 32 * dc.K : fc.W * 32 * fc.K;
+  const int TXP = wavefront ? dc.W * dc.CL * 32 * dc.K : fc.W * 32 * fc.K;
   const int cols_per_warp = 32 * (wavefront ? dc.K : fc.K);
   const long long fwd_smem = wavefront ? dc.sm.total : fc.sm.total;
 
@@ -991,10 +1010,10 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     int dp2_hs = 0;
     if (!fused && dc.linear && dc.skew <= 2 && dp2_selected(dc.K)) {
       dp2_hs = 32;
-      dp.warm = (g_tune_wf >= 16 ? g_tune_wf : kDp2Default) & 7;  // bit 0: instruction-cache warmer; bit 2: experiment (dummy mask walk)
+      dp.warm = dp2_flags() & 7;  // bit 0: instruction-cache warmer; bit 2: experiment (dummy mask walk)
     }
     if (!(g_debug_kernels & 8)) {  // (bit 3: watchdog test hook -- the backtrack kernel then never gets its words)
-      e = dp2_hs ? launch_dp2_k2(tmap, dp, dc.skew, st)
+      e = dp2_hs ? launch_dp2_k2(tmap, dp, dc.skew, dc.CL, st)
                  : launch_dp_dispatch(dc.K, tmap, dp, dc.skew, dc.linear != 0, st);
       if (e != cudaSuccess) return fail_at(e, __LINE__);
       count_launch();
