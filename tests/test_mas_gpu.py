@@ -181,6 +181,26 @@ def test_more_utterances_than_sms(mp, oracle):
         np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs), want)
 
 
+def test_wide_texts_on_clusters_in_waves_and_short_utterances(mp, oracle):
+    """Texts of more than four DP warps run on a cluster of two CTAs per utterance (mas_dp2.cuh): more clusters than the
+    machine holds at once (waves), and utterances far shorter than the padded text (t_x <= t_y << T_x: the second CTA's
+    columns are all padding, the first chunks lie above the diagonal)."""
+    rng = np.random.default_rng(321)
+    B, T_y, T_x = 100, 330, 320
+    nc = (rng.standard_normal((B, T_y, T_x)) * 2 - 1).astype(np.float32)
+    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+    for via in ("mask", "lengths"):
+        np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs, via=via), want)
+    B, T_y, T_x = 6, 90, 400
+    nc = (rng.standard_normal((B, T_y, T_x)) * 2 - 1).astype(np.float32)
+    t_ys = np.array([90, 70, 64, 33, 5, 1], np.int32)
+    t_xs = np.array([90, 40, 64, 32, 3, 1], np.int32)
+    want = oracle.maximum_path_numpy(nc, t_ys, t_xs).astype(np.int8)
+    for via in ("mask", "lengths"):
+        np.testing.assert_array_equal(_gpu_path(mp, nc, t_ys, t_xs, via=via), want)
+
+
 def test_back_to_back_calls_share_scratch(mp, oracle):
     """Consecutive calls overlap through programmatic dependent launch and reuse one scratch buffer:
     enqueue many without synchronising, with and without the dense path, then check every result."""
