@@ -617,6 +617,31 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             assert out_cpu.dtype == torch.float32 and np.array_equal(
                 out_cpu.numpy().astype(np.int32), mas_oracle.maximum_path_numpy(nc_cpu[(py_steps - 1) % 2].numpy(), t_ys, t_xs))
+        # ... and the C entry on PAGEABLE arrays, which is what the reference's own wrapper hands its native core
+        # (np.zeros / astype(np.float32) results, __init__.py:14-15) and what the compiled binding receives: `values` is
+        # staged into a pinned mirror by the entry's host threads
+        pg_vals = [hv.clone() for hv in h_vals]
+        pg_paths = [torch.zeros(B, T_y, T_x, dtype=torch.int32) for _ in range(2)]
+
+        def pageable_step(i):
+            rc = L.mas_maximum_path_c_host(pg_paths[i % 2].data_ptr(), pg_vals[i % 2].data_ptr(), h_ty.data_ptr(),
+                                           h_tx.data_ptr(), B, T_y, T_x)
+            assert rc == 0, rc
+        for i in range(2):
+            pageable_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(py_steps):
+            pageable_step(i)
+        dtg = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtg, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert np.array_equal(pg_paths[(py_steps - 1) % 2].numpy(),
+                                  mas_oracle.maximum_path_numpy(pg_vals[(py_steps - 1) % 2].numpy(), t_ys, t_xs))
+        e2e["c_entry_pageable"] = {"value": world * B * py_steps / float(dtg.item()), "unit": UNIT, "steps": py_steps,
+                                   "api": "mas_maximum_path_c_host on ordinary (pageable) host arrays, paths zero-filled once"}
+        del pg_vals, pg_paths
         e2e["python_api"] = {"value": world * B * py_steps / float(dtp.item()), "unit": UNIT, "steps": py_steps,
                              "api": "vits_b200.maximum_path(neg_cent_cpu, mask_cpu): pageable CPU tensors in, new fp32 CPU "
                                     "tensor out (lengths from the mask on the host, mas_maximum_path_host inside)"}

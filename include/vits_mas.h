@@ -110,6 +110,8 @@ int mas_maximum_path(const float* neg_cent,
  * zero-filled, as np.zeros does.  Rows below t_ys[b] are written in full (zeros and ones).  Only `values` crosses the
  * link in full: the path comes back as the 4-byte-per-frame index and is written into `paths` by a small pool of host
  * threads of the library's own (MAS_HOST_THREADS, default min(8, cores/2)) while later groups are still in flight.
+ * `values` may be pageable (a plain numpy array): it is then staged into a pinned mirror by the same threads, ahead of
+ * the DMA (MAS_HOST_NOSTAGE=1 leaves the staging to the driver).
  * Uses internal streams and cached device/pinned buffers; not re-entrant (the reference has a single caller thread).
  * Returns 0, a MAS_E_* code, or MAS_STATUS_* bits << 8 when an utterance had invalid lengths.
  */

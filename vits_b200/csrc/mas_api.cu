@@ -61,6 +61,8 @@ struct HostCtx {
   void* d_index = nullptr;      // [B][T_y] int32 per-frame text position (index-only pipeline)
   int32_t* h_index = nullptr;   // pinned host copy of it
   size_t cap_index = 0;
+  float* h_stage = nullptr;     // pinned mirror of a PAGEABLE `values` (filled by the host threads)
+  size_t cap_stage = 0;
   void* d_lens = nullptr;
   void* d_scratch = nullptr;
   cudaEvent_t ev_in[kChunks] = {}, ev_k[kChunks] = {}, ev_idx[kChunks] = {};  // group c: inputs landed / kernels done / index on the host
@@ -76,6 +78,7 @@ void host_release() {
   if (g_host.d_paths) cudaFree(g_host.d_paths);
   if (g_host.d_index) cudaFree(g_host.d_index);
   if (g_host.h_index) cudaFreeHost(g_host.h_index);
+  if (g_host.h_stage) cudaFreeHost(g_host.h_stage);
   if (g_host.d_lens) cudaFree(g_host.d_lens);
   if (g_host.d_scratch) cudaFree(g_host.d_scratch);
   if (g_host.h_status) cudaFreeHost(g_host.h_status);
@@ -235,6 +238,11 @@ struct ExpandJob {
   const int32_t* t_xs;
   int T_y, T_x, es, zero_tail;
   unsigned long long one;
+  // pageable `values`: utterance b's first stage_rows[b] rows are copied into the pinned mirror by the pool
+  const float* values = nullptr;
+  float* stage = nullptr;
+  const int* stage_rows = nullptr;  // [B] rows to stage (the longest utterance of b's group)
+  const int* group_of = nullptr;    // [B]
 };
 
 void expand_utterance(const ExpandJob& j, int b) {
@@ -261,7 +269,16 @@ void expand_utterance(const ExpandJob& j, int b) {
   }
 }
 
-// Persistent worker pool (created on first use; the calling thread works too).  Tasks are utterances.
+void stage_utterance(const ExpandJob& j, int b) {
+  const size_t plane = static_cast<size_t>(j.T_y) * j.T_x;
+  const int rows = j.stage_rows[b];
+  if (rows > 0) memcpy(j.stage + plane * b, j.values + plane * b, static_cast<size_t>(rows) * j.T_x * sizeof(float));
+}
+
+// Persistent worker pool (created on first use; the calling thread works too).  A task is an utterance: t >= 0 =
+// materialise the dense path rows of utterance t from its index; t < 0 = copy the leading rows of utterance -1-t of a
+// PAGEABLE `values` into the pinned mirror (cudaMemcpyAsync from pageable memory stages through one driver thread at
+// ~10 GB/s; eight threads of ours reach the host's memory bandwidth, and the DMA then runs at the pinned rate).
 class ExpandPool {
  public:
   static ExpandPool& get() {
@@ -269,14 +286,15 @@ class ExpandPool {
     return pool;
   }
   int threads() const { return static_cast<int>(workers_.size()) + 1; }
-  void begin(const ExpandJob& job) {
+  void begin(const ExpandJob& job, int groups) {
     std::lock_guard<std::mutex> lk(m_);
     job_ = job;
     pending_.clear();
     head_ = 0;
     outstanding_ = 0;
+    stage_left_.assign(groups, 0);
   }
-  void add(int b0, int nb) {
+  void add(int b0, int nb) {  // path rows of utterances [b0, b0+nb)
     {
       std::lock_guard<std::mutex> lk(m_);
       for (int b = b0; b < b0 + nb; ++b) pending_.push_back(b);
@@ -284,19 +302,42 @@ class ExpandPool {
     }
     cv_.notify_all();
   }
-  void finish() {  // the caller helps, then waits for the stragglers
+  void add_staging(int c, int b0, int nb) {  // leading rows of group c's utterances into the pinned mirror
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      for (int b = b0; b < b0 + nb; ++b) pending_.push_back(-1 - b);
+      outstanding_ += nb;
+      stage_left_[c] += nb;
+    }
+    cv_.notify_all();
+  }
+  void wait_staged(int c) {  // the caller helps until group c's rows are in the mirror
     for (;;) {
-      int b;
+      int t;
       {
         std::unique_lock<std::mutex> lk(m_);
-        if (head_ < pending_.size()) b = pending_[head_++];
+        if (stage_left_[c] == 0) return;
+        if (head_ < pending_.size()) t = pending_[head_++];
+        else {
+          done_cv_.wait(lk, [&] { return stage_left_[c] == 0; });
+          return;
+        }
+      }
+      run(t);
+    }
+  }
+  void finish() {  // the caller helps, then waits for the stragglers
+    for (;;) {
+      int t;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        if (head_ < pending_.size()) t = pending_[head_++];
         else {
           done_cv_.wait(lk, [&] { return outstanding_ == 0; });
           return;
         }
       }
-      expand_utterance(job_, b);
-      complete_one();
+      run(t);
     }
   }
 
@@ -319,27 +360,31 @@ class ExpandPool {
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
-  void complete_one() {
+  void run(int t) {
+    if (t >= 0) expand_utterance(job_, t);
+    else stage_utterance(job_, -1 - t);
     std::lock_guard<std::mutex> lk(m_);
-    if (--outstanding_ == 0) done_cv_.notify_all();
+    bool wake = --outstanding_ == 0;
+    if (t < 0 && --stage_left_[job_.group_of[-1 - t]] == 0) wake = true;
+    if (wake) done_cv_.notify_all();
   }
   void loop() {
     for (;;) {
-      int b;
+      int t;
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return stop_ || head_ < pending_.size(); });
         if (stop_) return;
-        b = pending_[head_++];
+        t = pending_[head_++];
       }
-      expand_utterance(job_, b);
-      complete_one();
+      run(t);
     }
   }
   std::vector<std::thread> workers_;
   std::mutex m_;
   std::condition_variable cv_, done_cv_;
   std::vector<int> pending_;
+  std::vector<int> stage_left_;
   size_t head_ = 0;
   int outstanding_ = 0;
   bool stop_ = false;
@@ -424,14 +469,69 @@ static int host_run(void* paths, int path_dtype, int zero_tail, const float* val
   MAS_CUDA(cudaMemcpyAsync(d_tx, t_xs, B * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
   MAS_CUDA(cudaMemsetAsync(g_host.d_scratch, 0, sc_one * ng, s_in));
   ExpandPool* pool = dense_d2h ? nullptr : &ExpandPool::get();
-  if (pool) pool->begin(ExpandJob{static_cast<unsigned char*>(paths), h_index, t_ys, t_xs, T_y, T_x, es, zero_tail,
-                                  one_pattern(path_dtype)});
+  // A pageable `values` (a plain numpy array, as the reference's wrapper passes: __init__.py:14) is copied into a pinned
+  // mirror by the host threads, group by group ahead of the DMA: cudaMemcpyAsync from pageable memory goes through one
+  // staging thread of the driver (python API with CPU tensors: 10.4 k alignments/s); MAS_HOST_NOSTAGE=1 restores that.
+  static const bool no_stage = getenv("MAS_HOST_NOSTAGE") && atoi(getenv("MAS_HOST_NOSTAGE")) != 0;
+  bool staged = false;
+  if (pool && !no_stage) {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, values) != cudaSuccess) cudaGetLastError();
+    else staged = pa.type == cudaMemoryTypeUnregistered;
+  }
+  std::vector<int> stage_rows, group_of;
+  if (staged) {
+    if (plane * B > g_host.cap_stage) {
+      if (g_host.h_stage) cudaFreeHost(g_host.h_stage);
+      g_host.h_stage = nullptr;
+      g_host.cap_stage = 0;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&g_host.h_stage), plane * B * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        staged = false;  // no pinned memory to spare: the driver's own staging it is
+      } else {
+        g_host.cap_stage = plane * B;
+      }
+    }
+  }
+  if (staged) {
+    stage_rows.resize(B);
+    group_of.resize(B);
+    for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
+      int rows = 0;
+      for (int b = b0; b < b0 + gsize[c]; ++b) rows = t_ys[b] > rows ? t_ys[b] : rows;
+      rows = rows > T_y ? T_y : (rows < 0 ? 0 : rows);
+      for (int b = b0; b < b0 + gsize[c]; ++b) {
+        stage_rows[b] = rows;
+        group_of[b] = c;
+      }
+    }
+  }
+  if (pool) {
+    ExpandJob job{static_cast<unsigned char*>(paths), h_index, t_ys, t_xs, T_y, T_x, es, zero_tail, one_pattern(path_dtype)};
+    if (staged) {
+      job.values = values;
+      job.stage = g_host.h_stage;
+      job.stage_rows = stage_rows.data();
+      job.group_of = group_of.data();
+    }
+    pool->begin(job, ng);
+    if (staged)
+      for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) pool->add_staging(c, b0, gsize[c]);
+  }
+  const float* h_values = staged ? g_host.h_stage : values;
+  struct Drain {  // no early return may leave workers behind that still read this call's arrays
+    ExpandPool* p;
+    ~Drain() {
+      if (p) p->finish();
+    }
+  } drain{pool};
   int nused = 0;
   for (int c = 0, b0 = 0; c < ng; b0 += gsize[c], ++c) {
     const int nb = gsize[c];
     cudaStream_t s_k = g_host.streams[1 + (c & 1)];
     unsigned char* sc = static_cast<unsigned char*>(g_host.d_scratch) + sc_one * c;
-    MAS_CUDA(copy_leading_rows(d_values, values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
+    if (staged) pool->wait_staged(c);
+    MAS_CUDA(copy_leading_rows(d_values, h_values, t_ys, b0, nb, T_y, T_x, cudaMemcpyHostToDevice, s_in));
     MAS_CUDA(cudaEventRecord(g_host.ev_in[c], s_in));
     MAS_CUDA(cudaStreamWaitEvent(s_k, g_host.ev_in[c], 0));
     if (dense_d2h)
