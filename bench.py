@@ -830,7 +830,7 @@ def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=5):
     names = ["fwd_first_start", "fwd_last_dp_done", "fwd_last_end", "bt_first_start", "bt_last_end",
              "wo_first_start", "wo_last_zero_fill_done", "wo_last_end|wavefront:lengths_known",
              "bt_top_group_words_seen", "bt_all_tables_done", "bt_chain_over_groups_done", "bt_last_table_done",
-             "bt_top_group_walked", "bt_last_table_words_complete"]
+             "bt_top_group_walked", "bt_last_table_words_complete", "bt16_walk_windows_loaded", "bt16_groups_rewalked"]
     tl = torch.zeros(16, dtype=torch.int64, device=dev)   # 16 slots (include/vits_mas.h: mas_set_timeline)
     out = {}
     try:

@@ -227,7 +227,7 @@ void mas_set_tuning2(int fused, int helpers);
  * ring_slots = chunks of 32 frames per warp (>= skew + 2, or 3); cols_per_lane in {1,2,4}; 0 = automatic. */
 void mas_set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane);
 /* Debug timeline: device pointer to 16 uint64 (slots 0,3,5 preset to ~0, the others to 0) that the
- * kernels update with min start / max end %globaltimer stamps (slots 8-13: phases of the backtrack kernel's
+ * kernels update with min start / max end %globaltimer stamps (slots 8-15: phases of the backtrack kernel's
  * tail, tools/timeline_gap.py); NULL disables. */
 void mas_set_timeline(void* dev_ptr);
 /* Debug event trace of the forward kernel's CTA 0 (-DMAS_TRACE builds, tools/trace_dp.py): device pointer to

@@ -153,20 +153,22 @@ def test_streaming_backtrack_with_16_bit_tables(mp, oracle):
     """Long utterances: the streaming backtrack keeps 16-bit exit columns and re-walks the groups."""
     L = mp._lib.lib()
     rng = np.random.default_rng(4096)
-    B, T_y, T_x = 2, 5000, 300
-    nc = (rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)
-    t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
-    want = oracle.maximum_path_numpy(nc, t_ys, t_xs)
-    try:
-        for mode in (2, -1, 0):
-            L.mas_set_tuning2(mode, 0)
-            ncd = torch.from_numpy(nc).cuda()
-            got = mp.maximum_path_from_lengths(ncd, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
-            np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want, err_msg=f"mode {mode}")
-            idx = mp.maximum_path_index(ncd, y_lengths=torch.as_tensor(t_ys), x_lengths=torch.as_tensor(t_xs))
-            np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want), err_msg=f"mode {mode}")
-    finally:
-        L.mas_set_tuning2(-1, 0)
+    # (2, 5000, 300): every group's 32-word walk window fits in shared memory next to the tables; (1, 4800, 512): it does
+    # not, the groups are re-walked from the scratch
+    for B, T_y, T_x in ((2, 5000, 300), (1, 4800, 512)):
+        nc = (rng.standard_normal((B, T_y, T_x)) * 3).astype(np.float32)
+        t_ys, t_xs = random_lengths(rng, B, T_y, T_x)
+        want = oracle.maximum_path_numpy(nc, t_ys, t_xs)
+        try:
+            for mode in (2, -1, 0):
+                L.mas_set_tuning2(mode, 0)
+                ncd = torch.from_numpy(nc).cuda()
+                got = mp.maximum_path_from_lengths(ncd, torch.as_tensor(t_ys), torch.as_tensor(t_xs))
+                np.testing.assert_array_equal(got.cpu().numpy().astype(np.int32), want, err_msg=f"mode {mode} {T_y}x{T_x}")
+                idx = mp.maximum_path_index(ncd, y_lengths=torch.as_tensor(t_ys), x_lengths=torch.as_tensor(t_xs))
+                np.testing.assert_array_equal(idx.cpu().numpy(), path_to_index(want), err_msg=f"mode {mode} {T_y}x{T_x}")
+        finally:
+            L.mas_set_tuning2(-1, 0)
 
 
 def test_more_utterances_than_sms(mp, oracle):

@@ -34,12 +34,17 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   constexpr uint32_t ROWB = 32u * K * 4u;      // bytes of one ring row: this warp's 32*K columns of one frame
   constexpr uint32_t SLOTB = R * ROWB;
   // CL > 1: an utterance's columns are split over a cluster of CL CTAs (W = DP warps of THIS CTA, global warp index
-  // gw0 + dw): the last column crosses the CTA boundary through distributed shared memory, by READS only -- the right
-  // CTA's first warp loads its hand-off blocks and the left neighbour's progress counter from the left CTA's shared
-  // memory (two blocks ahead: a remote load takes ~215 cycles), the left CTA's last warp reads the right neighbour's
-  // counter there.  (Remote STORES were tried first: a store per step through shared::cluster cost ~20 cycles each and
-  // the fence.acq_rel.cluster in front of the progress store 0.7 us per superstep: c3 94 instead of 43 us.)  A text of
-  // 512 tokens is then four DP warps per SM (one per scheduler, linear ring) instead of eight on one SM with the
+  // gw0 + dw): the last column crosses the CTA boundary through distributed shared memory, by READS only, and not by a
+  // DP warp -- a COURIER warp of the right CTA polls the progress counter of the left CTA's last warp, copies each new
+  // block of 32 hand-off values from the left CTA's ring into the local one (ring 0, unused otherwise) and publishes
+  // its own counter, so that the right CTA's first DP warp sees an ordinary local neighbour; the left CTA's last warp
+  // reads the courier's counter for back-pressure (one remote load per superstep).  History: remote STORES first (a
+  // store per step through shared::cluster ~20 cycles each, fence.acq_rel.cluster in front of the progress store
+  // 0.7 us per superstep: c3 94 instead of 43 us); then remote LOADS by the DP warp itself, two blocks ahead -- but a
+  // remote load takes ~215 cycles and shares its scoreboard with the step's shuffles and ring loads (six scoreboards
+  // for everything in flight), so every wait for a shuffle also waited for the remote load: the boundary warp's 32
+  // steps took 1237 instead of 917 cycles and the whole chain ran at its pace (profiles/r02bi_c4_trace.txt).  A text
+  // of 512 tokens is then four DP warps per SM (one per scheduler, linear ring) instead of eight on one SM with the
   // select ring of the first generation.
   const int rank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int b = CL > 1 ? blockIdx.x / CL : blockIdx.x;
@@ -48,6 +53,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   const bool spread = p.W <= 3;  // warp roles exactly as in mas_dp_kernel
   const int NP = p.W <= 3 ? 2 : 4;
   int dw = spread ? (wid < 3 ? (wid < p.W ? wid : -1) : (wid & 3) == 3 ? p.W + (wid >> 2) : -1) : wid;
+  if (CL > 1 && !spread && wid == p.W + NP + 1) dw = -1;  // the extra warp of a cluster launch: courier (rank > 0) or filler
   const int lane = tid & 31;
   const int S = p.S, W = p.W, BR = p.BR;
   const int gw0 = rank * W;  // global index of this CTA's first DP warp
@@ -55,6 +61,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   // the instruction-cache warmer: an idle warp on the scheduler of the last DP warp (which starts last)
   const bool shadow = (p.warm & 1) != 0 && spread && wid == (W < 3 ? 4 + W : 6);
   const int dwa = shadow ? 0 : dw;  // whose ring / barriers a warp addresses
+  const int cour_wid = (CL > 1 && rank > 0) ? (spread ? 9 : W + NP + 1) : -1;
+  const bool courier = wid == cour_wid;
 
   unsigned char* ring_all = smem + p.sm.ring;
   unsigned char* ringw = ring_all + static_cast<size_t>(dwa < 0 ? 0 : dwa) * nphys * SLOTB;
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before the TMA's later writes
   }
   for (int i = tid; i < (W + 1) * BR; i += blockDim.x) bnd[i] = (i == 0 && rank == 0) ? 0.0f : kNeg;  // (0,0): v_prev = 0 (core.pyx:22-23)
-  if (tid < W) prog[tid] = 0;
+  if (tid <= W) prog[tid] = 0;  // ([W]: the courier's counter)
   volatile int* lens_v = lens_s;  // [0] t_y, [1] t_x, [2] 1 once they are known
   if (tid == 0) {
     lens_s[2] = 0;
@@ -161,8 +169,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   // round trip when every thread issues a handful of loads instead of two batches of sixteen by one warp.
   const bool lenw = dw == W + NP;
   const bool dummy_walk = (p.warm & 4) != 0 && p.t_ys != nullptr && p.mask != nullptr;  // (experiment: the walk's traffic alone)
-  const bool helper = spread && dw < 0 && !shadow && (p.t_ys == nullptr || dummy_walk);
-  if (dw < 0 && !shadow && !helper) {  // filler warps
+  const bool helper = spread && dw < 0 && !shadow && !courier && (p.t_ys == nullptr || dummy_walk);
+  if (dw < 0 && !shadow && !helper && !courier) {  // filler warps
     leave();
     return;
   }
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
       if (spread) {
         for (int u = 0; u < 12; ++u) {
           const bool sh = (p.warm & 1) != 0 && u == (W < 3 ? 4 + W : 6);
-          const bool part = u == 11 || (!sh && ((u < 3 && u >= W) || (u > 3 && (u & 3) != 3)));
+          const bool part = u != cour_wid && (u == 11 || (!sh && ((u < 3 && u >= W) || (u > 3 && (u & 3) != 3))));
           nh += part ? 1 : 0;
           hrank += part && u < wid ? 1 : 0;
         }
@@ -246,6 +254,42 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
       nchunks = (t_y + R - 1) / R;
     }
   };
+  if (CL > 1 && courier) {
+    // ---- courier: the left CTA's last column, block by block, into ring 0 of this CTA ----
+    // The left warp's superstep s publishes slots 32(s-Q)+R0 .. +31 of its ring and then progress s+1; `n` mirrors that
+    // counter: chunk n (0-based) may be copied once the remote counter is past it and the local first warp has left the
+    // slots it overwrites (the left warp's own rule for its right neighbour, need_r below).
+    constexpr int R0 = 32 * Q - (31 * D - 1);
+    const uint32_t lrank = static_cast<uint32_t>(rank > 0 ? rank - 1 : 0);
+    const uint32_t rprog = ptx::mapa(ptx::smem_u32(&prog[W - 1]), lrank);
+    const uint32_t rbnd = ptx::mapa(ptx::smem_u32(bnd + static_cast<size_t>(W) * BR), lrank);
+    int n = 0;
+    for (;;) {
+      check_lens();
+      const int lim = min(ptx::ld_volatile_cluster_s32(rprog), ptx::ld_volatile_s32(&prog[0]) + BR / 32);
+      if (lim > n) {
+        while (n < lim) {
+          const int m = min(lim - n, 4);
+          float x[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < m) x[k] = ptx::ld_volatile_cluster_f32(rbnd + 4u * static_cast<uint32_t>((32 * (n + k - Q) + R0 + lane) & (BR - 1)));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < m) ptx::st_volatile_f32(bnd + ((32 * (n + k - Q) + R0 + lane) & (BR - 1)), x[k]);
+          n += m;
+        }
+        __syncwarp();
+        if (lane == 0) ptx::st_volatile_s32(&prog[W], n);
+        __nanosleep(300);  // the next block is most of a superstep (~600 ns) away
+        continue;
+      }
+      if (known && n >= NS) break;
+      __nanosleep(150);
+    }
+    leave();
+    return;
+  }
   if (dw >= W && !shadow) {
     // ---- producer warps: unchanged from mas_dp_kernel ----
     const int q = dw - W;
@@ -283,21 +327,18 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   const int x0 = (gw * 32 + lane) * K;
   const bool has_left = gw > 0;
   const bool has_right = gw < W * CL - 1 && !shadow;
-  // progress of the neighbours and the left edge: this CTA's shared memory, or (CL > 1, the warps either side of the
-  // CTA boundary) the neighbouring CTA's, as shared::cluster addresses
-  const bool in_remote = CL > 1 && dwa == 0 && rank > 0;
+  // progress of the neighbours and the left edge: this CTA's shared memory -- the first warp of a right CTA has the
+  // courier (counter prog[W], ring 0) for a left neighbour; the last warp of a left CTA reads the right CTA's courier
+  // counter through a shared::cluster address
   const bool right_remote = CL > 1 && dwa == W - 1 && rank < CL - 1;
-  const int* plp = &prog[dwa > 0 ? dwa - 1 : 0];
+  const int* plp = (CL > 1 && dwa == 0 && rank > 0) ? &prog[W] : &prog[dwa > 0 ? dwa - 1 : 0];
   const int* prp = &prog[dwa < W - 1 ? dwa + 1 : 0];
-  const uint32_t plc = CL > 1 ? (in_remote ? ptx::mapa(ptx::smem_u32(&prog[W - 1]), rank - 1) : ptx::mapa(ptx::smem_u32(plp), rank)) : 0u;
-  const uint32_t prc = CL > 1 ? (right_remote ? ptx::mapa(ptx::smem_u32(&prog[0]), rank + 1) : ptx::mapa(ptx::smem_u32(prp), rank)) : 0u;
-  auto ld_left = [&]() { return CL > 1 ? ptx::ld_volatile_cluster_s32(plc) : ptx::ld_volatile_s32(plp); };
+  const uint32_t prc = CL > 1 ? (right_remote ? ptx::mapa(ptx::smem_u32(&prog[W]), rank + 1) : ptx::mapa(ptx::smem_u32(prp), rank)) : 0u;
+  auto ld_left = [&]() { return ptx::ld_volatile_s32(plp); };
   auto ld_right = [&]() { return CL > 1 ? ptx::ld_volatile_cluster_s32(prc) : ptx::ld_volatile_s32(prp); };
   const bool lane0 = lane == 0;
   const bool lane31 = lane == 31 && !shadow;
-  const uint32_t bnd_in = CL > 1 ? (in_remote ? ptx::mapa(ptx::smem_u32(bnd + static_cast<size_t>(W) * BR), rank - 1)
-                                            : ptx::mapa(ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR), rank))
-                                 : ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR);
+  const uint32_t bnd_in = ptx::smem_u32(bnd + static_cast<size_t>(dwa) * BR);
   float* bnd_out = bnd + static_cast<size_t>(dwa + 1) * BR;
   uint2* bits_b = reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP + x0;  // {word, tag} pairs
   const int dt = x0 + D * lane;
@@ -323,8 +364,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   int ls = 0;
   uint32_t par = 0u;
 
-  constexpr int NE = CL > 1 ? 4 : 2;  // hand-off blocks of 8 frames held in registers ...
-  constexpr int AH = CL > 1 ? 2 : 1;  // ... loaded this many blocks ahead of their use
+  constexpr int NE = 2;  // hand-off blocks of 8 frames held in registers ...
+  constexpr int AH = 1;  // ... loaded this many blocks ahead of their use
   float cb[4][K], e[NE][8];
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -337,8 +378,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   bool pre = false;
 
   auto load_e = [&](uint32_t a, float (&e8)[8]) {
-    const float4 e0 = CL > 1 ? ptx::ld_cluster_f32x4(a) : ptx::lds_f32x4(a);
-    const float4 e1 = CL > 1 ? ptx::ld_cluster_f32x4(a + 16u) : ptx::lds_f32x4(a + 16u);
+    const float4 e0 = ptx::lds_f32x4(a);
+    const float4 e1 = ptx::lds_f32x4(a + 16u);
     e8[0] = e0.x; e8[1] = e0.y; e8[2] = e0.z; e8[3] = e0.w;
     e8[4] = e1.x; e8[5] = e1.y; e8[6] = e1.z; e8[7] = e1.w;
   };
@@ -389,6 +430,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     }
     if (has_right && need_r > 0)
       while (ld_right() < need_r) {
+        check_lens();  // (a right neighbour that knew the lengths first stops at NS: nothing left to wait for then)
+        if (known && s >= NS) break;
       }
     ea += static_cast<uint32_t>(fl) >> 31;  // (null) dependency: the hand-off loads stay behind the poll
 #pragma unroll
@@ -400,7 +443,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   auto superstep = [&](int s, auto diag_tag) {
     constexpr bool DIAG = decltype(diag_tag)::value;
 #ifdef MAS_TRACE
-    unsigned long long* tr = (p.trace && b == 0 && lane0 && s < 256 && !shadow) ? p.trace + (static_cast<size_t>(dwa) * 256 + s) * 8 : nullptr;
+    unsigned long long* tr = (p.trace && b == 0 && lane0 && s < 256 && !shadow) ? p.trace + (static_cast<size_t>(gw) * 256 + s) * 8 : nullptr;
     if (tr) tr[0] = clock64();
 #endif
     emit_words(s - 1 - Q, s - 1 >= Q && !shadow);
@@ -526,7 +569,7 @@ inline cudaError_t launch_dp2_t(const CUtensorMap& tmap, const DpParams& p, cuda
   if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024, attr_set); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.B * CL);
-  cfg.blockDim = dim3(p.W <= 3 ? 32 * 12 : 32 * (p.W + 4 + 1));
+  cfg.blockDim = dim3(p.W <= 3 ? 32 * 12 : 32 * (p.W + 4 + 1 + (CL > 1 ? 1 : 0)));  // (+ the courier warp)
   cfg.dynamicSmemBytes = p.sm.total;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -566,16 +566,69 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     // group's words from the scratch (L2-resident)
     if (idx_b)
       for (int y = t_y + tid; y < p.T_y; y += blockDim.x) idx_b[y] = -1;
-    for (int g = tid; g <= g_top; g += blockDim.x) {
-      const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
-      int cur = sentry[g];
+    // A group's walk starts at its entry and moves left by at most one column per frame: the 32 words at and to the
+    // left of the entry are all it can read.  The warps fetch them into shared memory first, eight groups' loads in
+    // flight per warp -- a thread re-walking its group straight from the scratch paid 32 dependent L2 round trips
+    // (c4: 9.7 us after the chain over the groups, profiles/r02_final_bench_c4.json).
+    uint32_t* swin = reinterpret_cast<uint32_t*>(smisc + 16);  // [G][32] (dec16 == 2)
+    if (p.dec16 == 2) {
+      for (int g0 = warp; g0 < g_top; g0 += 8 * nw) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int g = g0 + i * nw;
+          w8[i] = 0u;
+          if (g < g_top) {
+            const int c = sentry[g] - lane;
+            if (c >= 0) w8[i] = load_tagged(bits_b + static_cast<size_t>(g) * p.TXP + c).x;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int g = g0 + i * nw;
+          if (g < g_top) swin[g * 32 + lane] = w8[i];
+        }
+      }
+      __syncthreads();
+      if (tid == 0) tl_max(p.tl, 14);
+    }
+    if (p.dec16 == 2) {
+      // one thread per group walks it in shared memory and leaves the group's 32 decisions as one word (in the first
+      // slot of its own window); the frames are then written as with 32-bit tables, by all threads
+      for (int g = tid; g < g_top; g += blockDim.x) {
+        const uint32_t* win = swin + g * 32;
+        uint32_t m = 0u;
+        int off = 0;
+#pragma unroll 8
+        for (int r = 31; r >= 0; --r) {
+          const uint32_t bit = (win[off] >> (31 - r)) & 1u;
+          m |= bit << r;
+          off += static_cast<int>(bit);
+        }
+        swin[g * 32] = m;
+      }
+      __syncthreads();
+      if (tid == 0) tl_max(p.tl, 15);
       const uint32_t topw = static_cast<uint32_t>(smisc[3]);
-      for (int r = (g == g_top) ? ((t_y - 1) & 31) : 31; r >= 0; --r) {
-        const int y = (g << 5) + r;
-        if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + cur) * p.es, p.es, p.one);
-        if (idx_b) idx_b[y] = cur;
-        const uint32_t bit = (g == g_top) ? (topw >> r) & 1u : (load_tagged(row + cur).x >> (31 - r)) & 1u;
-        cur -= static_cast<int>(bit);
+      for (int y = tid; y < t_y; y += blockDim.x) {
+        const int g = y >> 5, r = y & 31;
+        const uint32_t dec = g == g_top ? topw : swin[g * 32];
+        const int v = sentry[g] - __popc(static_cast<uint32_t>(static_cast<unsigned long long>(dec) >> (r + 1)));
+        if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + v) * p.es, p.es, p.one);
+        if (idx_b) idx_b[y] = v;
+      }
+    } else {
+      for (int g = tid; g <= g_top; g += blockDim.x) {
+        const uint2* row = bits_b + static_cast<size_t>(g) * p.TXP;
+        int cur = sentry[g];
+        const uint32_t topw = static_cast<uint32_t>(smisc[3]);
+        for (int r = (g == g_top) ? ((t_y - 1) & 31) : 31; r >= 0; --r) {
+          const int y = (g << 5) + r;
+          if (path_b) store_one(path_b + (static_cast<size_t>(y) * p.T_x + cur) * p.es, p.es, p.one);
+          if (idx_b) idx_b[y] = cur;
+          const uint32_t bit = (g == g_top) ? (topw >> r) & 1u : (load_tagged(row + cur).x >> (31 - r)) & 1u;
+          cur -= static_cast<int>(bit);
+        }
       }
     }
   }
@@ -936,6 +989,10 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
   if (bs_smem > 200 * 1024) {  // long utterances: 16-bit exit columns instead of 32-bit decision words
     dec16 = 1;
     bs_smem = (static_cast<size_t>(G_) * TXS / 2 + 1 + static_cast<size_t>(bt_warps) * TXS + G_ + 16) * 4;
+    if (bs_smem + static_cast<size_t>(G_) * 128 <= 200 * 1024) {  // room for every group's 32-word walk window
+      dec16 = 2;
+      bs_smem += static_cast<size_t>(G_) * 128;
+    }
   }
   const bool stream_ok = bs_smem <= 200 * 1024 && (g_debug_kernels & 7) == 7;
   int mode = g_tune_fused;

@@ -143,6 +143,11 @@ __device__ __forceinline__ int ld_volatile_cluster_s32(uint32_t addr) {
   asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ float ld_volatile_cluster_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.volatile.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
