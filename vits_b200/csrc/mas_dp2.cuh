@@ -533,19 +533,28 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     while (NS == 0 && !known) check_lens();
   }
   if (s < NS) {
+    int lim = 0;  // supersteps below this one start on `pre` alone
     if (!pre) blocking_start(s);
     for (;;) {
       if (s >= sd0 && s <= sd1) superstep(s, std::true_type{});
       else superstep(s, std::false_type{});
       ++s;
       if (s == 1 && gw == 0 && lane0 && !shadow) bnd[0] = kNeg;  // the (0,0) special case is consumed
-      if (pre && known && s < NS) continue;  // the common case: everything the next superstep needs is there
+      // The common case: everything the next superstep needs is there.  While the lengths are still unknown (taken from
+      // the mask they arrive ~10 us into a c2 call, 40 us into a c4 call) the DP warps look for them every eighth
+      // superstep only: the look costs ~80 cycles on the lone warp's critical path (c4: 2.6 us per call), and nothing
+      // here needs them before the utterance's last frame -- a warp that learns them late runs at most seven supersteps
+      // past a short utterance's end, on padding, like every warp does before they arrive.  (Probing the flag inside the
+      // superstep's block instead: one more volatile load in the body, +0.5 us at c2 with the lengths given.)  `lim` folds
+      // "known and s < NS" and "unknown and not yet the eighth" into the one comparison the loop had before.
+      if (pre && s < lim) continue;
       if (!known) check_lens();
       if (s >= NS) {
         if (known) break;
         while (!known) check_lens();  // ran through every frame that exists before the lengths arrived
         if (s >= NS) break;
       }
+      lim = known ? NS : min(NS, (s | 7) + 1);
       if (!pre) blocking_start(s);
     }
     if (!shadow) emit_words(s - 1 - Q, s - 1 >= Q);  // the last group's words
