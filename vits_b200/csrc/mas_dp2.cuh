@@ -23,6 +23,20 @@
 #pragma once
 #include "mas_dp.cuh"
 
+// How the diagonal x == y (core.pyx:17-18 `v_cur = max_neg_val`, :32 `index == y`) is handled.  1: cells ABOVE the
+// diagonal add 0 instead of their neg_cent value (a select on the ring value, off the recurrence's dependency chain), so
+// everything above the diagonal stays at exactly the sentinel -- which is then what a diagonal cell finds as v_cur -- and
+// the forced decision bit is OR-ed into the group's finished word.  0: the first form -- per step, the running value is
+// replaced by the sentinel and the bit forced where i == the lane's diagonal step (two selects on the chain: a
+// diagonal superstep's 32 steps took 1350 instead of 780 cycles, and with one warp after the other crossing the
+// diagonal the LAST warp's first seven supersteps all ran at that pace: profiles/r02bj_c2_trace.txt).
+#ifndef MAS_DIAGC
+#define MAS_DIAGC 1
+#endif
+// (Tried and dropped: lane 31 collecting four frames of the last column and publishing them as one 16-byte store --
+// eight hand-off stores per superstep instead of 32: the block's 32 steps took 765 instead of 753 cycles and the code
+// between two blocks 300 instead of 262, c2 +1.0 us, c4 +3.5 us; profiles/r02bk_handoff_16_byte_stores.txt.)
+
 namespace mas {
 
 template <int K, int D, int CL>
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
 
   // The decision words of group g = s-Q are complete after superstep s: frames 32g+r of lane l sit in hist[Q-a] (the
   // older part) and hist[Q-a-1], a = D*l/32, shifted by D*l % 32.  One 16-byte store of two {word, tag} pairs.
-  auto emit_words = [&](int g, bool on) {
+  auto emit_words = [&](int g, bool on, auto force_tag) {
     uint32_t w[K];
 #pragma unroll
     for (int jj = 0; jj < K; ++jj) {
@@ -397,6 +411,8 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
         lo = (hsel == a) ? hist[Q - a - 1][jj] : lo;
       }
       w[jj] = __funnelshift_l(lo, hi, hsh);
+      if (MAS_DIAGC && decltype(force_tag)::value)  // core.pyx:32 `index == y`: frame x of column x steps
+        w[jj] |= (g == ((x0 + jj) >> 5)) ? (0x80000000u >> ((x0 + jj) & 31)) : 0u;
     }
     if (x0 == 0) w[0] = 0u;  // core.pyx:32 `index != 0`
     uint2* dst = bits_b + static_cast<long long>(g) * p.TXP;
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     unsigned long long* tr = (p.trace && b == 0 && lane0 && s < 256 && !shadow) ? p.trace + (static_cast<size_t>(gw) * 256 + s) * 8 : nullptr;
     if (tr) tr[0] = clock64();
 #endif
-    emit_words(s - 1 - Q, s - 1 >= Q && !shadow);
+    emit_words(s - 1 - Q, s - 1 >= Q && !shadow, diag_tag);
 #pragma unroll
     for (int k = Q; k >= 1; --k)
 #pragma unroll
@@ -480,10 +496,12 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
         if (has_right) pr = ld_right();
         dep = static_cast<uint32_t>(pl) >> 31;  // (null) dependency: the prefetch of the next block 0 stays behind this probe
       }
-      const float (&c)[K] = cb[i & 3];
+      float c[K];
+#pragma unroll
+      for (int jj = 0; jj < K; ++jj) c[jj] = (MAS_DIAGC && DIAG && i < dd + jj) ? 0.0f : cb[i & 3][jj];  // (above the diagonal)
       const float nxt = __shfl_up_sync(0xffffffffu, v[K - 1], 1);  // for step i+D
       const float le = lane0 ? e[(i / 8) & (NE - 1)][i & 7] : left[0];
-      if (DIAG) {
+      if (!MAS_DIAGC && DIAG) {
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) v[jj] = (i == dd + jj) ? kNeg : v[jj];  // core.pyx:17-18
       }
@@ -496,7 +514,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
       const float d = v[0] - le;
       hist[0][0] = __funnelshift_l(__float_as_uint(d), hist[0][0], 1);
       v[0] = c[0] + fmaxf(le, v[0]);
-      if (DIAG) {
+      if (!MAS_DIAGC && DIAG) {
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) hist[0][jj] |= (i == dd + jj) ? 1u : 0u;  // core.pyx:32 `index == y`
       }
@@ -520,7 +538,11 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
 #endif
   };
 
-  const int sd0 = diag_lo >> 5, sd1 = diag_hi >> 5;  // supersteps in which the diagonal x == y crosses this warp's columns
+  // supersteps in which the diagonal x == y crosses this warp's columns.  MAS_DIAGC: the variant runs from superstep 0
+  // (every cell above the diagonal must stay at the sentinel) until the words of the last group that holds a diagonal
+  // cell of these columns have left (group 2gw+1, emitted at the start of superstep 2gw+2+Q).
+  const int sd0 = MAS_DIAGC ? 0 : diag_lo >> 5;
+  const int sd1 = MAS_DIAGC ? max(diag_hi >> 5, ((diag_lo + 32 * K - 1) >> 5) + 1 + Q) : diag_hi >> 5;
   int s = 0;
   if (shadow) {  // one superstep of the plain variant, far from any diagonal, on whatever the ring holds
     s = sd1 + 1;
@@ -557,7 +579,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
       lim = known ? NS : min(NS, (s | 7) + 1);
       if (!pre) blocking_start(s);
     }
-    if (!shadow) emit_words(s - 1 - Q, s - 1 >= Q);  // the last group's words
+    if (!shadow) emit_words(s - 1 - Q, s - 1 >= Q, std::true_type{});  // the last group's words
   }
   if (shadow) {
     leave();
