@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   double* red = reinterpret_cast<double*>(smem + p.sm.red);
   int* lens_s = reinterpret_cast<int*>(red + 64);
 
+  if (p.use_tma && tid == 0) ptx::prefetch_tensormap(&tmap);  // (the descriptor's fetch overlaps the barrier set-up)
   ptx::pdl_wait();
   const long long rows_total = static_cast<long long>(p.B) * p.T_y;
   auto copy_chunk = [&](int w, int c, unsigned char* dst, uint64_t* bar) {

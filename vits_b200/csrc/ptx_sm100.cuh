@@ -68,6 +68,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
       : "memory");
 }
 
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- Ampere-style 4-byte async copy with zero fill (src_bytes 0 or 4), completion on an mbarrier ----
 __device__ __forceinline__ void cp_async4_zfill(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
