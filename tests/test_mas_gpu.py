@@ -311,6 +311,32 @@ def test_invalid_lengths_flagged_not_imitated(mp):
     assert mp.maximum_path_from_lengths(nc, torch.tensor([20, 20, 20]), torch.tensor([12, 9, 4]), check=True).sum().item() == 60
 
 
+def test_invalid_lengths_on_a_cluster_sized_text(mp, oracle):
+    """The same, where an utterance runs on a cluster of two CTAs with a courier warp at the boundary (mas_dp2.cuh): empty
+    and t_x > t_y utterances next to valid ones, lengths given and taken from the mask -- every warp of both CTAs must
+    find its way out, and the valid utterances keep their exact paths."""
+    rng = np.random.default_rng(99)
+    B, T_y, T_x = 6, 500, 400
+    nc = (rng.standard_normal((B, T_y, T_x)) * 2).astype(np.float32)
+    t_ys = np.array([500, 0, 120, 33, 400, 1], np.int32)
+    t_xs = np.array([400, 300, 200, 33, 399, 1], np.int32)       # utterance 2: t_x > t_y; utterance 1: empty
+    ok = [0, 3, 4, 5]
+    want = oracle.maximum_path_numpy(nc[ok], t_ys[ok], t_xs[ok]).astype(np.int8)
+    ncd = torch.from_numpy(nc).cuda()
+    ty, tx = torch.as_tensor(t_ys).cuda(), torch.as_tensor(t_xs).cuda()
+    mask = ((torch.arange(T_y, device="cuda")[None, :] < ty[:, None])[:, :, None]
+            & (torch.arange(T_x, device="cuda")[None, :] < tx[:, None])[:, None, :]).float()
+    for rep in range(3):
+        mp.last_status()
+        for out in (mp.maximum_path_from_lengths(ncd, ty, tx), mp.maximum_path(ncd, mask)):
+            got = out.cpu().numpy().astype(np.int8)
+            np.testing.assert_array_equal(got[ok], want)
+            assert got[1].sum() == 0 and got[2].sum() == 0
+        bits = mp.last_status()
+        assert bits & 1 and bits & 2 and not bits & 8
+    assert (mp.status_nosync(reset=True) & 3) == 3   # (the device-wide mirror saw them too; left clean for the next test)
+
+
 def test_raw_c_abi_overwrites_output_and_respects_stream(mp, oracle):
     L = mp._lib.lib()
     rng = np.random.default_rng(31)
