@@ -863,7 +863,7 @@ def per_kernel_ms(L, ncs, mask, B, T_y, T_x, dev, reps=5):
                     med[n] = float(np.median(vals))
             out["pdl" if pdl else "serialised"] = med
     finally:
-        L.mas_set_tuning(0, 0, 0, 1)
+        L.mas_set_tuning(0, 0, 0, -1)
         L.mas_set_timeline(None)
     return out
 

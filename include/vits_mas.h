@@ -207,8 +207,9 @@ uint64_t mas_launch_count(void);
 
 /* Benchmark/tuning hooks (not part of the reference-facing surface); 0 = automatic choice.
  * cols_per_lane in {1,2,4,8}; rows_per_stage in {8,16,32}; stages >= 2; pdl: 0 = ordinary launches,
- * 1 (default) = programmatic dependent launch between the kernels of one call, 2 = the forward kernel is
- * launched programmatically too (behind the previous kernel of the stream; measured slower). */
+ * 1 = programmatic dependent launch between the kernels of one call, 2 = the forward kernel is launched
+ * programmatically too, behind the previous kernel of the stream; negative (default) = 2 where that was measured
+ * to pay (wavefront forward kernel + streaming backtrack kernel), 1 elsewhere. */
 void mas_set_tuning(int cols_per_lane, int rows_per_stage, int stages, int pdl);
 /* neg_cent implementation: -1 automatic, 0 fp32 CUDA cores, 1 tcgen05 (split-bf16). */
 void mas_set_neg_cent_impl(int impl);

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def mp():
     import vits_b200.monotonic_align as m
     yield m
-    m._lib.lib().mas_set_tuning(0, 0, 0, 1)
+    m._lib.lib().mas_set_tuning(0, 0, 0, -1)
     m._lib.lib().mas_set_tuning2(-1, 0)
 
 
@@ -88,7 +88,7 @@ def test_every_kernel_configuration(mp, oracle, K, R):
             L.mas_set_tuning2(fused, helpers)
             got = _gpu_path(mp, nc, t_ys, t_xs)
             np.testing.assert_array_equal(got, want, err_msg=f"K={K} R={R} S={stages} pdl={pdl} fused={fused} {shape}")
-    L.mas_set_tuning(0, 0, 0, 1)
+    L.mas_set_tuning(0, 0, 0, -1)
     L.mas_set_tuning2(-1, 0)
 
 
@@ -113,7 +113,7 @@ def test_wavefront_forward_kernel_configurations(mp, oracle, K, ring_mode):
                 got = _gpu_path(mp, nc, t_ys, t_xs)
                 np.testing.assert_array_equal(got, want, err_msg=f"K={K} ring={ring_mode} S={slots} pdl={pdl} {shape}")
     finally:
-        L.mas_set_tuning(0, 0, 0, 1)
+        L.mas_set_tuning(0, 0, 0, -1)
         L.mas_set_tuning2(-1, 0)
         L.mas_set_tuning3(-1, 0, 0, 0)
 

@@ -17,6 +17,8 @@ MODES = [(1, 0), (32, 0), (33, 0), (33, 1), (1, 1)]   # (wavefront mode, ring mo
 if "--modes" in sys.argv:
     MODES = [tuple(int(y) for y in x.split(":")) for x in sys.argv[sys.argv.index("--modes") + 1].split(",")]
 L = _lib.lib()
+if "--pdl1" in sys.argv:   # the forward kernel launched ordinarily (mas_set_tuning pdl = 1; default: behind the previous call)
+    L.mas_set_tuning(0, 0, 0, 1)
 if "--no-fuzz" not in sys.argv:
     rng = np.random.default_rng(5)
     shapes = [(2, 900, tx) for tx in (24, 64, 100, 128, 192, 256, 300, 384, 512)] + [(3, 333, 300), (2, 64, 60), (2, 33, 20), (1, 5, 4),

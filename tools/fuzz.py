@@ -18,7 +18,7 @@ for shape in shapes:
     res = []
     for mode in (0,):
         for stream in (0, 1, 2, 3, -1):
-            L.mas_set_tuning(0, 0, 0, 1); L.mas_set_tuning2(stream, 0)
+            L.mas_set_tuning(0, 0, 0, -1); L.mas_set_tuning2(stream, 0)
             nbad = 0; err = ""
             for rep in range(4):
                 try:

@@ -48,6 +48,6 @@ def main():
             print(f"K={K} R={R:2d} fused={F} H={H}: forward {t1:7.1f} us | +backtrack {t3:7.1f} | +writeout {t7:7.1f} us | all PDL {t7p:7.1f} us")
         except Exception as e:
             print(f"K={K} R={R} failed: {e}")
-    L.mas_set_debug_kernels(7); L.mas_set_tuning(0, 0, 0, 1); L.mas_set_tuning2(-1, 0)
+    L.mas_set_debug_kernels(7); L.mas_set_tuning(0, 0, 0, -1); L.mas_set_tuning2(-1, 0)
 
 main()

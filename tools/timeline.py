@@ -47,4 +47,4 @@ for mode in ('eager', 'graph'):
             reset(); gr.replay()
             show(f"{wl} graph pdl={pdl}")
             L.mas_set_timeline(None)
-L.mas_set_tuning(0, 0, 0, 1)
+L.mas_set_tuning(0, 0, 0, -1)

@@ -23,7 +23,7 @@ tls = [torch.zeros(16, dtype=torch.int64, device='cuda') for _ in range(N)]
 def reset():
     for tl in tls:
         tl.zero_(); tl[0] = tl[3] = tl[5] = -1
-L.mas_set_tuning(0, 0, 0, 0 if '--pdl0' in sys.argv else 2 if '--xpdl' in sys.argv else 1)
+L.mas_set_tuning(0, 0, 0, 0 if '--pdl0' in sys.argv else 2 if '--xpdl' in sys.argv else 1 if '--pdl1' in sys.argv else -1)
 use_mask = '--mask' in sys.argv   # lengths from a [B,T_y,T_x] fp32 mask (the reference's signature) instead of given
 if use_mask:
     mask = ((torch.arange(T_y, device='cuda')[None, :] < ty[:, None])[:, :, None]

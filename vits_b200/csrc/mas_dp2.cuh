@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
   int* lens_s = reinterpret_cast<int*>(red + 64);
 
   if (p.use_tma && tid == 0) ptx::prefetch_tensormap(&tmap);  // (the descriptor's fetch overlaps the barrier set-up)
-  ptx::pdl_wait();
   const long long rows_total = static_cast<long long>(p.B) * p.T_y;
   auto copy_chunk = [&](int w, int c, unsigned char* dst, uint64_t* bar) {
     if (p.use_tma) {
@@ -119,31 +118,14 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     if (!p.use_tma) ptx::cp_async_mbar_arrive_noinc(bar);
   };
 
+  // Everything that touches only this CTA's shared memory comes BEFORE the wait: launched programmatically behind the
+  // previous call (mas_set_tuning pdl = 2, the default) the CTA is resident while that call's backtrack kernel drops its
+  // ones, and has its barriers, rings and counters ready when the wait returns.
   const int nspec = min(2, (p.T_y + R - 1) / R);
-  if (dw == W) {
-    if (lane == 0) {
-      for (int i = 0; i < W * S; ++i) ptx::mbar_init(&full_all[i], p.use_tma ? 1 : 32);
-      ptx::mbar_fence_init();
-    }
-    __syncwarp();
-    for (int c = 0; c < nspec; ++c)
-      for (int w = 0; w < W; ++w) issue_chunk(w, c, c);
+  if (dw == W && lane == 0) {
+    for (int i = 0; i < W * S; ++i) ptx::mbar_init(&full_all[i], p.use_tma ? 1 : 32);
+    ptx::mbar_fence_init();
   }
-  if (blockIdx.x == 0 && tid == 0) {
-    p.wo_counters[0] = 0;
-    p.wo_counters[1] = 0;
-  }
-  constexpr uint32_t tag = 1u;
-  if (p.lenstag) {
-    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
-    const int n16 = p.G * p.TXP / 2;
-    for (int i = tid + rank * blockDim.x; i < n16; i += blockDim.x * CL) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0 && rank == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
-  }
-  if (tid == 0) tl_min(p.tl, 0);
-#ifdef MAS_TRACE
-  if (p.trace && tid == 0) p.trace[8 * 256 * 8 + 2 * b] = globaltimer_ns();
-#endif
   // Frames < 0: the Q ring slots that precede chunk 0 (slots S-Q .. S-1 of every warp's ring) read as zero, so
   // a lane whose skew has not brought it to frame 0 yet computes 0 + max(sentinel, sentinel): its row stays at
   // the sentinel without a select per step.  (The producers refill those slots only after superstep Q-1, by
@@ -165,6 +147,27 @@ __global__ void __launch_bounds__(CL > 1 ? 384 : 416, 1) mas_dp2_kernel(const __
     red[0] = 0.0;
     red[1] = 0.0;
   }
+  ptx::pdl_wait();  // global memory is first touched from here on
+  if (dw == W) {
+    __syncwarp();
+    for (int c = 0; c < nspec; ++c)
+      for (int w = 0; w < W; ++w) issue_chunk(w, c, c);
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    p.wo_counters[0] = 0;
+    p.wo_counters[1] = 0;
+  }
+  constexpr uint32_t tag = 1u;
+  if (p.lenstag) {
+    uint4* z = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.bits) + static_cast<size_t>(b) * p.G * p.TXP);
+    const int n16 = p.G * p.TXP / 2;
+    for (int i = tid + rank * blockDim.x; i < n16; i += blockDim.x * CL) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0 && rank == 0) *reinterpret_cast<unsigned long long*>(p.lenstag + b) = 0ull;
+  }
+  if (tid == 0) tl_min(p.tl, 0);
+#ifdef MAS_TRACE
+  if (p.trace && tid == 0) p.trace[8 * 256 * 8 + 2 * b] = globaltimer_ns();
+#endif
   __syncthreads();
   // A peer reads this CTA's hand-off ring and progress counters: nobody starts before both CTAs are initialised, and
   // nobody leaves (leave() below) before both are done.

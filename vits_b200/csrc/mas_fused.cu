@@ -35,7 +35,7 @@ FusedLayout fused_layout(int B, int C, int T_y, int T_x) {
   neg_cent_tc_dims(C, T_y, T_x, &L.Nt, &L.NTL, &L.MT);
   L.RT = L.MT;  // the ring holds every frame block: the producer never has to wait for the consumer
   L.pitch = L.NTL * L.Nt;
-  L.zstride = L.MT + 1;  // per utterance: MT tile flags + the fill flag
+  L.zstride = L.MT + 1;  // words per utterance: MT tile counters + one fill flag (laid out as [B][MT] then [B])
   auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
   L.off_tc = 0;
   L.tc_bytes = up(neg_cent_tc_scratch_bytes(B, C, T_y, T_x));
@@ -87,7 +87,12 @@ int stats_to_path(const float* z_p, const float* m_p, const float* logs_p, const
   float* ring = reinterpret_cast<float*>(sc + L.off_ring);
 
   // Ask the search first whether it can take a streamed source at this shape (nothing is launched on refusal).
-  FusedSrc fs{ring, L.pitch, L.RT, L.MT, flags, L.NTL, flags + L.MT, L.zstride, gemm_ctas};
+  // flags: [B][MT] tile counters (indexed b * MT + mt by both kernels), then [B] fill flags -- B * zstride words in all,
+  // which is what the prep kernel clears.  (The fill flags used to sit at flags + MT with stride MT + 1, i.e. INSIDE the
+  // tile counters for B > 1: utterance 0's fill flag was utterance 1's first tile counter, the backtrack kernel then did
+  // not wait for the zero-fill, and about one call in a hundred at B = 2, T_y = 1100 lost the ones of its last frames
+  // to a late zero -- tools/stress_streamed_small.py.)
+  FusedSrc fs{ring, L.pitch, L.RT, L.MT, flags, L.NTL, flags + static_cast<size_t>(B) * L.MT, 1, gemm_ctas};
   TcStream so{ring, flags, t_ys, t_xs, L.RT, L.pitch, n1 > 0 ? sms : gemm_ctas, gemm_ctas, n1, flags, L.zstride};
   int rc = maximum_path(ring, t_ys, t_xs, nullptr, 0, 0, 0, 0, path_out, path_dtype, index_out, sc + L.off_mas, L.mas_bytes,
                         B, T_y, T_x, st, &fs, /*probe_only=*/true);

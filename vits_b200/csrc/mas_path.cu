@@ -304,7 +304,6 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
   int* sentry = reinterpret_cast<int*>(sstage + static_cast<size_t>(nw) * p.TXS);  // [G]
   int* smisc = sentry + p.G;                                                // [5]: t_y, t_x, entry below the top group, top decisions, timed out
 
-  ptx::pdl_launch_dependents();  // the next call's forward kernel may set up while we run
   if (tid == 0) tl_min(p.tl, 3);
   // Watchdog: everything this kernel polls is produced by EARLIER kernels of the stream, so a poll can only
   // fail to terminate if one of them died (or the context was descheduled for seconds).  Give up after 2 s rather
@@ -512,6 +511,11 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
     if (lane == 0) tl_max(p.tl, 12);
   }
   __syncthreads();  // all tables are in shared memory
+  // Whatever follows in the stream (the next call's forward kernel, when that is launched programmatically:
+  // mas_set_tuning pdl = 2) may be scheduled from here on: only the chain over the groups and the ones are left, about
+  // as long as a launch takes -- and the forward CTAs of THIS call are gone, so the early CTAs take nobody's SM.  (At the
+  // top of the kernel the trigger let the next call's forward CTAs become resident one by one during this call.)
+  ptx::pdl_launch_dependents();
   if (tid == 0) tl_max(p.tl, 9);
   if (*dead) {  // a poll gave up: nothing derived from incomplete words leaves this kernel
     if (idx_b)
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(512, 2) mas_backtrack_stream_kernel(const BsPa
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = 1, g_tune_fused = -1, g_tune_H = 0;
+static int g_tune_K = 0, g_tune_R = 0, g_tune_S = 0, g_tune_pdl = -1, g_tune_fused = -1, g_tune_H = 0;
 static int g_tune_wf = -1, g_tune_ring = 0, g_tune_wfS = 0, g_tune_wfK = 0;  // wavefront forward kernel (mas_set_tuning3)
 static int g_fill_div = 4;  // streaming mode: fill CTAs = g_fill_div/4 x SM count (tunable through MAS_FILL_DIV)
 static int g_debug_kernels = 7;  // bit0 forward, bit1 backtrack, bit2 write-out (benchmark isolation only); bit3: skip the
@@ -892,7 +896,7 @@ static cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_tune_pdl ? 1 : 0;
+  cfg.numAttrs = g_tune_pdl != 0 ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -1039,7 +1043,9 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     dp.mask = mask; dp.mask_dtype = mask_dtype; dp.msb = msb; dp.msy = msy; dp.msx = msx;
     dp.lens = lens; dp.status = status; dp.mirror = mirror; dp.bits = bits; dp.lenstag = lenstag; dp.tl = g_timeline; dp.trace = g_trace;
     dp.wo_counters = fused ? nullptr : status + 4;
-    dp.pdl = fused ? 1 : g_tune_pdl == 2;  // see set_tuning: the forward kernel is an ordinary launch by default
+    // see set_tuning: behind the previous call when asked for, or by default in the measured configuration (streaming
+    // backtrack kernel, whose trigger comes late)
+    dp.pdl = fused ? 1 : (g_tune_pdl == 2 || (g_tune_pdl < 0 && stream));
     if (fused) {  // launched programmatically behind the contraction kernel and fed by it tile by tile
       dp.tile_flags = fused->tile_flags; dp.tile_need = fused->tile_need; dp.RT = fused->RT; dp.MT = fused->MT;
       dp.fill_out = static_cast<unsigned char*>(path_out);
@@ -1194,17 +1200,20 @@ void set_timeline(unsigned long long* dev_ptr) { g_timeline = dev_ptr; }
 unsigned long long* timeline_ptr() { return g_timeline; }
 void set_trace(unsigned long long* dev_ptr) { g_trace = dev_ptr; }
 
-// pdl: 0 = every kernel an ordinary launch; 1 (default) = write-out and backtrack kernels launched
-// programmatically behind the forward kernel of their call, the forward kernel itself ordinarily; 2 = the
-// forward kernel programmatically too, behind whatever precedes it in the stream.  2 was the default until it
-// was measured call by call (tools/timeline_gap.py, four calls in one graph, c2 full-length): the next call's
-// forward CTAs then become resident one by one as SMs drain during the current call, and the DP of every call
-// but the first takes 40-44 us instead of 33 us -- far more than the ~1.3 us of launch latency the edge hides.
+// pdl: 0 = every kernel an ordinary launch; 1 = write-out and backtrack kernels launched programmatically behind the
+// forward kernel of their call, the forward kernel itself ordinarily; 2 = the forward kernel programmatically too,
+// behind whatever precedes it in the stream; negative (default) = 2 for the wavefront forward kernels followed by the
+// streaming backtrack kernel (the configuration measured below), 1 otherwise.  History: 2 with the backtrack kernel's trigger at its TOP let the
+// next call's forward CTAs become resident one by one as SMs drained during the current call, and the DP of every
+// call but the first took 40-44 us instead of 33 us (tools/timeline_gap.py, four calls in one graph) -- so 1 became the
+// default.  With the trigger AFTER the backtrack kernel's tables (only the chain over the groups and the ones are
+// left, the call's forward CTAs are gone) and the forward kernel's shared-memory set-up in front of its wait, 2 is
+// 0.15-0.3 us per call faster than 1 at c2/c3/c4 (profiles/r02bo_forward_behind_previous_call.txt).
 void set_tuning(int K, int R, int S, int pdl) {
   g_tune_K = K;
   g_tune_R = R;
   g_tune_S = S;
-  g_tune_pdl = pdl;
+  g_tune_pdl = pdl;  // (negative: automatic)
 }
 void set_tuning3(int wavefront, int ring_mode, int ring_slots, int cols_per_lane) {
   g_tune_wf = wavefront;
