@@ -1140,8 +1140,12 @@ int maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs
     wp.ones = stream ? 0 : 1;
     // few enough CTAs that all of them are resident at once on the SMs the forward kernel leaves idle
     // (they all have to run phase B; a CTA that starts only after the forward kernel adds tail latency)
-    // (streaming mode has the whole DP time for the fill: fewer CTAs = less HBM contention for the forward kernel)
-    const int fill_ctas = (stream ? g_fill_div : 2) * g_num_sms / (stream ? 4 : 1);
+    // (streaming mode has the whole DP time for the fill: fewer CTAs = less HBM contention for the forward kernel -- but
+    // the fill must not outlast the DP.  With the lengths GIVEN the DP of a c2 call ends at ~22 us, the fill of its
+    // 50 MB at one CTA per SM at ~25 us: half as many CTAs again take 0.8 us off the call; with the lengths from the
+    // mask the DP ends later and the extra CTAs only cost.  profiles/r02bs_fill_cta_sweep.txt)
+    const int fill_div = fill_div_env ? g_fill_div : (t_ys != nullptr ? 6 : g_fill_div);
+    const int fill_ctas = (stream ? fill_div : 2) * g_num_sms / (stream ? 4 : 1);
     int grid = wp.nchunks < fill_ctas ? wp.nchunks : fill_ctas;
     if (grid < 1) grid = 1;
     // Dynamic shared memory the write-out does not use: just enough that its CTAs cannot be co-resident
