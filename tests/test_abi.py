@@ -107,3 +107,32 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "mas_oracle" not in text, f
+
+
+def test_lengths_from_a_cpu_mask_match_the_reference_expression():
+    """The host side of `maximum_path(neg_cent_cpu, mask_cpu)`: `mask.sum(1)[:, 0]` / `mask.sum(2)[:, 0]`
+    (monotonic_align/__init__.py:17-18) from column 0 / row 0 only, for every mask dtype a caller can hand in -- exact
+    counts also where a half-precision sum would round (t_y > 2048)."""
+    import numpy as np
+    import torch
+    from vits_b200.monotonic_align import _lengths_from_mask_cpu
+    T_y, T_x = 4100, 40
+    ty = torch.tensor([4099, 2049, 17, 0])
+    tx = torch.tensor([40, 33, 1, 0])
+    prefix = (torch.arange(T_y)[None, :] < ty[:, None])[:, :, None] & (torch.arange(T_x)[None, :] < tx[:, None])[:, None, :]
+    for dt in (torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.bool, torch.uint8, torch.int64):
+        m = prefix.to(dt)
+        got_y, got_x = _lengths_from_mask_cpu(m)
+        assert got_y.dtype == torch.int32 and got_x.dtype == torch.int32
+        assert got_y.tolist() == ty.tolist() and got_x.tolist() == tx.tolist(), dt
+    # and literally the reference's expression where that is exact
+    m = prefix.float()
+    ref_y = m.sum(1)[:, 0].numpy().astype(np.int32)
+    ref_x = m.sum(2)[:, 0].numpy().astype(np.int32)
+    got_y, got_x = _lengths_from_mask_cpu(m)
+    assert np.array_equal(got_y.numpy(), ref_y) and np.array_equal(got_x.numpy(), ref_x)
+    # a strided (non-contiguous) mask view is accepted as it is
+    wide = torch.zeros(4, T_y, 2 * T_x)
+    wide[:, :, ::2] = m
+    got_y, got_x = _lengths_from_mask_cpu(wide[:, :, ::2])
+    assert got_y.tolist() == ty.tolist() and got_x.tolist() == tx.tolist()
