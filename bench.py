@@ -714,7 +714,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes,
-                         "kernel": "maximum_path chain (mas_dp wavefront forward kernel + mas_writeout zero-fill + "
+                         "kernel": "maximum_path chain (mas_dp2 wavefront forward kernel + mas_writeout zero-fill + "
                                    "mas_backtrack_stream, concurrent on disjoint SMs through programmatic dependent launch, "
                                    "timed as one unit with CUDA events on the launching stream)",
                          "phase_timeline_us": kernels_ms},
